@@ -1,0 +1,80 @@
+"""Build libbevfront_b200.so (hand-written CUDA for sm_100a behind a C ABI) in-tree with nvcc.
+
+    python -m bevfusion_3d_object_detection_b200.build [-f] [-v]
+
+The library has no torch / Python dependency; nvcc cross-compiles it without a GPU.  The built .so is
+git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libbevfront_b200.so")
+OBJDIR = os.path.join(HERE, "build")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I" + INCLUDE, "-I" + CSRC,
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; libbevfront_b200.so cannot be built")
+    return exe
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps():
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(INCLUDE, "bevfront_b200.h"))
+    return deps
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
+                and os.path.getmtime(obj) > hdr_t):
+            return obj
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed on " + src)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,20 @@
+// capi.cu -- ABI bookkeeping for libbevfront_b200 (version, last-error text).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace bevf {
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+}  // namespace bevf
+
+BEVF_API int bevf_abi_version(void) { return 1; }
+BEVF_API const char *bevf_last_error(void) { return bevf::g_last_error; }
+BEVF_API int bevf_compiled_arch(void) { return 100; }

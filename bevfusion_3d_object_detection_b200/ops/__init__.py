@@ -1,0 +1,6 @@
+"""Same public names as the reference's projects/BEVFusion/bevfusion/ops/__init__.py:1-4."""
+from .bev_pool import BevPoolTables, bev_pool, bev_pool_fused
+from .voxel import DynamicScatter, Voxelization, dynamic_scatter, voxelization
+
+__all__ = ["bev_pool", "Voxelization", "voxelization", "dynamic_scatter", "DynamicScatter", "bev_pool_fused",
+           "BevPoolTables"]

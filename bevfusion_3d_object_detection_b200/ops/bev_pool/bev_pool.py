@@ -1,0 +1,211 @@
+"""bev_pool() and its autograd functions with the reference's surface
+(projects/BEVFusion/bevfusion/ops/bev_pool/bev_pool.py:7-172), plus the fused north-star form
+(`BevPoolTables`, `bev_pool_fused`) in which depth x context, the kept / sort gathers, the interval sum,
+the permute and the collapse-Z of depth_lss.py:184-202, 723-725 are one kernel.
+"""
+import torch
+
+from ..._lib import check, cur_stream, lib, ptr
+from . import bev_pool_ext
+
+
+def _interval_table(ranks, n):
+    """interval starts / lengths of a rank-sorted sequence (bev_pool.py:46-55, 154-159)."""
+    first = torch.ones(n, device=ranks.device, dtype=torch.bool)
+    first[1:] = ranks[1:] != ranks[:-1]
+    starts = torch.where(first)[0].int()
+    lengths = torch.empty_like(starts)
+    lengths[:-1] = starts[1:] - starts[:-1]
+    lengths[-1] = n - starts[-1]
+    return starts, lengths
+
+
+class QuickCumsum(torch.autograd.Function):
+    """Pure-torch cumsum formulation (bev_pool.py:7-34); kept for API parity, not used by bev_pool()."""
+
+    @staticmethod
+    def forward(ctx, x, geom_feats, ranks):
+        csum = x.cumsum(0)
+        last = torch.ones(x.shape[0], device=x.device, dtype=torch.bool)
+        last[:-1] = ranks[1:] != ranks[:-1]
+        csum, geom_feats = csum[last], geom_feats[last]
+        pooled = torch.cat((csum[:1], csum[1:] - csum[:-1]))
+        ctx.save_for_backward(last)
+        ctx.mark_non_differentiable(geom_feats)
+        return pooled, geom_feats
+
+    @staticmethod
+    def backward(ctx, gradx, gradgeom):
+        (last,) = ctx.saved_tensors
+        owner = torch.cumsum(last, 0)
+        owner[last] -= 1
+        return gradx[owner], None, None
+
+
+class QuickCumsumTrainingCuda(torch.autograd.Function):
+    """bev_pool.py:43-90: forward builds the interval table from `ranks`; backward broadcasts out_grad."""
+
+    @staticmethod
+    def forward(ctx, x, geom_feats, ranks, B, D, H, W):
+        starts, lengths = _interval_table(ranks, x.shape[0])
+        geom_feats = geom_feats.int()
+        out = bev_pool_ext.bev_pool_forward(x.contiguous(), geom_feats.contiguous(), lengths, starts, int(B), int(D),
+                                            int(H), int(W))
+        ctx.save_for_backward(starts, lengths, geom_feats)
+        ctx.saved_shapes = int(B), int(D), int(H), int(W)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        starts, lengths, geom_feats = ctx.saved_tensors
+        B, D, H, W = ctx.saved_shapes
+        x_grad = bev_pool_ext.bev_pool_backward(out_grad.contiguous(), geom_feats.contiguous(), lengths, starts, B, D,
+                                                H, W)
+        return x_grad, None, None, None, None, None, None
+
+
+class QuickCumsumCuda(torch.autograd.Function):
+    """bev_pool.py:93-143: inference-only form taking the interval table; ONNX symbolic
+    `autoware::QuickCumsumCuda` with the same attribute names."""
+
+    @staticmethod
+    def symbolic(g, x, geom_feats, interval_lengths, interval_starts, B, D, H, W):
+        from torch.onnx.symbolic_helper import _get_tensor_dim_size, _get_tensor_sizes
+
+        output = g.op("autoware::QuickCumsumCuda", x, geom_feats, interval_lengths, interval_starts,
+                      batch_size_i=B, dimension_i=D, height_i=H, width_i=W, outputs=1)
+        if _get_tensor_sizes(x) is not None and hasattr(x.type(), "with_sizes"):
+            output.setType(x.type().with_sizes([B, D, H, W, _get_tensor_dim_size(x, -1)]))
+        return output
+
+    @staticmethod
+    def forward(ctx, x, geom_feats, interval_lengths, interval_starts, B, D, H, W):
+        return bev_pool_ext.bev_pool_forward(x.contiguous(), geom_feats.contiguous(), interval_lengths,
+                                             interval_starts, B, D, H, W)
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        raise NotImplementedError
+
+
+def _as_int(v):
+    return int(v.item()) if isinstance(v, torch.Tensor) else int(v)
+
+
+def bev_pool(feats, coords, ranks, B, D, H, W, is_training):
+    """bev_pool.py:146-172.  feats[Nk,C] / coords[Nk,4] (x,y,z,b) / ranks[Nk] sorted by rank ->
+    [B, C, D, H, W] contiguous.  D, H, W may be python ints, 0-dim tensors or nn.Parameters."""
+    assert feats.shape[0] == coords.shape[0]
+    if is_training:
+        x = QuickCumsumTrainingCuda.apply(feats, coords, ranks, _as_int(B), _as_int(D), _as_int(H), _as_int(W))
+    else:
+        starts, lengths = _interval_table(ranks, feats.shape[0])
+        if coords.dtype != torch.int32:
+            coords = coords.int()
+        x = QuickCumsumCuda.apply(feats, coords, lengths, starts, _as_int(B), _as_int(D), _as_int(H), _as_int(W))
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# Fused form
+# ------------------------------------------------------------------------------------------------------
+class BevPoolTables:
+    """Per-calibration index tables of the fused kernel, derived from the reference's own
+    `bev_pool_aux` outputs (depth_lss.py:118-176; the deploy path precomputes exactly these once per rig,
+    deploy/voxel_detection.py:98-106):
+
+      src            [nk]      int32  frustum index (into B*N*D*fH*fW) of each kept point, rank-sorted
+      interval_starts[n_int+1] int32  CSR offsets into src
+      interval_cell  [n_int]   int32  output cell (b*nz+z)*nx*ny + x*ny + y, ascending
+      cell_of_point  [N']      int32  output cell of every frustum point or -1 (backward)
+    """
+
+    def __init__(self, geom_feats, kept, ranks, indices, B, nz, nx, ny):
+        dev = geom_feats.device
+        nk = geom_feats.shape[0]
+        kept_idx = torch.nonzero(kept.reshape(-1), as_tuple=False).squeeze(1)
+        src = kept_idx[indices]
+        g = geom_feats.long()
+        cell = (g[:, 3] * nz + g[:, 2]) * (nx * ny) + g[:, 0] * ny + g[:, 1]
+        # the fused kernel walks cells in memory order: re-sort by cell (stable), which for B == 1, nz == 1 is
+        # already the rank order
+        if nk > 1 and bool((cell[1:] < cell[:-1]).any()):
+            cell, perm = torch.sort(cell, stable=True)
+            src = src[perm]
+        first = torch.ones(nk, device=dev, dtype=torch.bool)
+        if nk > 0:
+            first[1:] = cell[1:] != cell[:-1]
+        starts = torch.nonzero(first, as_tuple=False).squeeze(1)
+        self.n_intervals = int(starts.numel())
+        self.nk = int(nk)
+        self.src = src.int().contiguous()
+        self.interval_cell = cell[starts].int().contiguous()
+        self.interval_starts = torch.cat([starts, starts.new_tensor([nk])]).int().contiguous()
+        nprime = kept.numel()
+        cop = torch.full((nprime,), -1, dtype=torch.int32, device=dev)
+        cop[src] = cell.int()
+        self.cell_of_point = cop
+        self.B, self.nz, self.nx, self.ny = int(B), int(nz), int(nx), int(ny)
+
+
+def nchw_to_nhwc(x):
+    """[N, C, H, W] contiguous -> [N, H, W, C] contiguous (library transpose kernel)."""
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().bevf_nchw_to_nhwc(ptr(x), ptr(out), int(n), int(c), int(h * w), cur_stream(x.device)))
+    return out
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().bevf_nhwc_to_nchw(ptr(x), ptr(out), int(n), int(c), int(h * w), cur_stream(x.device)))
+    return out
+
+
+class _BevPoolFused(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, depth, ctx_feats, tables):
+        # depth [BN, D, fH, fW], ctx_feats [BN, C, fH, fW] (NCHW, as the depthnet emits them)
+        depth = depth.contiguous()
+        ctx_nhwc = nchw_to_nhwc(ctx_feats.contiguous())
+        bn, d, fh, fw = depth.shape
+        c = ctx_feats.shape[1]
+        t = tables
+        out = torch.empty((t.B, c * t.nz, t.nx, t.ny), dtype=torch.float32, device=depth.device)
+        with torch.cuda.device(depth.device):
+            check(lib().bevf_bev_pool_fused_forward(ptr(depth), ptr(ctx_nhwc), ptr(t.src), ptr(t.interval_starts),
+                                                    ptr(t.interval_cell), t.n_intervals, t.nk, int(bn), int(d),
+                                                    int(fh), int(fw), int(c), t.B, t.nz, t.nx, t.ny, ptr(out),
+                                                    cur_stream(depth.device)))
+        ctx.save_for_backward(depth, ctx_nhwc)
+        ctx.tables = tables
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        depth, ctx_nhwc = ctx.saved_tensors
+        t = ctx.tables
+        bn, d, fh, fw = depth.shape
+        c = ctx_nhwc.shape[3]
+        dev = depth.device
+        out_grad = out_grad.contiguous()
+        g_nhwc = torch.empty((t.B * t.nz * t.nx * t.ny, c), dtype=torch.float32, device=dev)
+        d_depth = torch.empty_like(depth)
+        d_ctx_nhwc = torch.empty_like(ctx_nhwc)
+        with torch.cuda.device(dev):
+            L = lib()
+            check(L.bevf_nchw_to_nhwc(ptr(out_grad), ptr(g_nhwc), t.B, int(c), t.nz * t.nx * t.ny, cur_stream(dev)))
+            check(L.bevf_bev_pool_fused_backward(ptr(g_nhwc), ptr(depth), ptr(ctx_nhwc), ptr(t.cell_of_point), int(bn),
+                                                 int(d), int(fh), int(fw), int(c), ptr(d_depth), ptr(d_ctx_nhwc),
+                                                 cur_stream(dev)))
+        return d_depth, nhwc_to_nchw(d_ctx_nhwc), None
+
+
+def bev_pool_fused(depth, ctx_feats, tables):
+    """depth [B*N, D, fH, fW] (softmax), ctx_feats [B*N, C, fH, fW] -> [B, C*nz, nx, ny]; differentiable in
+    both inputs.  Equals depth_lss.py get_cam_feats' outer product followed by BaseViewTransform.bev_pool."""
+    return _BevPoolFused.apply(depth, ctx_feats, tables)

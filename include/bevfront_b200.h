@@ -1,0 +1,188 @@
+/*
+ * bevfront_b200.h -- C ABI of the B200-native BEV front-end library (libbevfront_b200.so).
+ *
+ * Drop-in boundary for the three data-parallel operators of BEVFusion's BEV feature construction:
+ * voxelization, bev_pool and sparse 3-D convolution.  Every entry point is `extern "C"`, takes plain
+ * device pointers + sizes + a CUDA stream (as void*), launches asynchronously on that stream and returns
+ * an int status (BEVF_OK == 0).  No torch / ATen types cross this boundary.  Each function cites the
+ * reference interface (paths relative to the reference repo root) it replaces; the bindings a maintainer
+ * adds on the reference side are shown in INTEGRATION.md.
+ *
+ * All pointers are device pointers unless a name ends in `_host`.  Tensors are dense, row-major, fp32 /
+ * int32 unless stated.  Workspaces are caller-owned scratch of at least the size the matching
+ * `*_workspace_bytes` call returns; they need no initialisation.
+ */
+#ifndef BEVFRONT_B200_H_
+#define BEVFRONT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEVF_OK 0
+#define BEVF_ERR_INVALID_ARGUMENT 1
+#define BEVF_ERR_CUDA 2
+#define BEVF_ERR_UNSUPPORTED 3
+#define BEVF_ERR_WORKSPACE 4
+
+#define BEVF_REDUCE_SUM 0 /* voxelization.h:4  typedef enum { SUM = 0, MEAN = 1, MAX = 2 } reduce_t */
+#define BEVF_REDUCE_MEAN 1
+#define BEVF_REDUCE_MAX 2
+
+/* ABI version (bumped when a signature changes) and the last error message of the calling thread. */
+int bevf_abi_version(void);
+const char *bevf_last_error(void);
+/* compute capability of the device the library was compiled for: 100 (sm_100a). */
+int bevf_compiled_arch(void);
+
+/* ------------------------------------------------------------------------------------------------ *
+ * Voxelization
+ * ------------------------------------------------------------------------------------------------ */
+
+/* grid_size[j] = round((range[3+j]-range[j]) / voxel_size[j]) in fp32
+ * (ops/voxel/src/voxelization_cuda.cu:257-259, ops/voxel/voxelize.py:108-112).  Host-only helper. */
+int bevf_voxel_grid_size(const float *voxel_size_host, const float *coors_range_host, int *grid_size_host);
+
+/*
+ * dynamic_voxelize  (ops/voxel/src/voxelization.h:83-95 -> dynamic_voxelize_gpu, voxelization_cuda.cu:485-528,
+ * kernel :25-61; pybind name `dynamic_voxelize`, voxelization.cpp:8).
+ * coors[N,3] int32 (x,y,z), written in place.  Out-of-range rows reproduce the reference kernel's partial
+ * writes: x fails -> coors[i,0] = -1 only; y fails -> [i,0:2] = -1; z fails -> all three -1 (the caller
+ * zero-fills, voxelize.py:42).  Only NDim == 3 is supported (the reference kernel hard-codes it too).
+ */
+int bevf_dynamic_voxelize(const float *points, int num_points, int num_features, int *coors,
+                          const float *voxel_size_host, const float *coors_range_host, int ndim, void *stream);
+
+/*
+ * hard_voxelize  (voxelization.h:58-81; deterministic: hard_voxelize_gpu voxelization_cuda.cu:231-373;
+ * non-deterministic: :375-483; pybind name `hard_voxelize`, voxelization.cpp:7).
+ *
+ * Semantics (bit-exact with the deterministic reference): voxel id = order of first appearance in point
+ * order; a point's slot = its rank among the points of the same voxel in point order; points with rank >=
+ * max_points and voxels with id >= max_voxels (and their points) are dropped;
+ * num_points_per_voxel = number of kept points.  voxels[max_voxels,max_points,C], coors[max_voxels,3],
+ * num_points_per_voxel[max_voxels] follow the reference contract: CALLER zero-fills them
+ * (voxelize.py:51-53) unless `zero_fill` != 0, in which case the library writes the zero padding of the
+ * first voxel_num voxels itself and the buffers may be uninitialised.
+ * deterministic == 0 is accepted and returns the same (deterministic) result, which is one of the
+ * outcomes the reference's racing kernels can produce.
+ * voxel_num is written to *voxel_num_dev (device int32).  The launch is asynchronous; the reference's
+ * `int` return value is obtained by copying that word to the host (bevf_hard_voxelize_sync does it).
+ */
+size_t bevf_hard_voxelize_workspace_bytes(int num_points, int max_points, int max_voxels);
+int bevf_hard_voxelize(const float *points, int num_points, int num_features, float *voxels, int *coors,
+                       int *num_points_per_voxel, const float *voxel_size_host, const float *coors_range_host,
+                       int max_points, int max_voxels, int ndim, int deterministic, int zero_fill,
+                       void *workspace, size_t workspace_bytes, int *voxel_num_dev, void *stream);
+/* same, then stream-synchronises and returns voxel_num through *voxel_num_host (the reference return value). */
+int bevf_hard_voxelize_sync(const float *points, int num_points, int num_features, float *voxels, int *coors,
+                            int *num_points_per_voxel, const float *voxel_size_host,
+                            const float *coors_range_host, int max_points, int max_voxels, int ndim,
+                            int deterministic, int zero_fill, void *workspace, size_t workspace_bytes,
+                            int *voxel_num_dev, void *stream, int *voxel_num_host);
+
+/*
+ * Extension: hard voxelization fused with BEVFusion.voxelize's mean reduce and batch-index
+ * pad (projects/BEVFusion/bevfusion/bevfusion.py:227-255 with voxelize_reduce=True):
+ *   feats[M,C] = sum over kept points / count, coords[M,4] = (batch_idx, x, y, z), sizes[M] = count.
+ * Same voxel order / drop rules as bevf_hard_voxelize.  The padded [max_voxels,max_points,C] tensor is
+ * never materialised.  Outputs are written at row offset *row_offset_dev (device int32, may be NULL = 0)
+ * so consecutive samples of a batch append without a host sync; *voxel_num_dev receives this sample's M
+ * and, when row_offset_dev is not NULL, *row_offset_dev += M afterwards.
+ */
+int bevf_voxelize_mean(const float *points, int num_points, int num_features, float *feats, int *coords4,
+                       int *sizes, const float *voxel_size_host, const float *coors_range_host, int max_points,
+                       int max_voxels, int batch_idx, void *workspace, size_t workspace_bytes,
+                       int *voxel_num_dev, int *row_offset_dev, void *stream);
+
+/*
+ * dynamic_point_to_voxel_forward / _backward  (voxelization.h:107-138 -> scatter_points_cuda.cu:183-308;
+ * pybind names voxelization.cpp:9-10).
+ * forward: rows of coors[N,ndim] with any negative component are dropped; unique rows are emitted in
+ * ascending lexicographic order (at::unique_dim sorted=true); reduced[M,C] = max / sum / mean of the
+ * points of each row; coors_map[N] = row of each point or -1; reduce_count[M].  Output buffers are
+ * sized for N rows; M is written to *num_out_dev.  ndim in 1..4.
+ * Two-step call (the reference synchronises inside unique_dim as well):
+ *   1. bevf_dynamic_scatter_extents -> extents_dev[4] = per-column (max over valid rows) + 1; copy to host
+ *   2. bevf_dynamic_scatter_workspace_bytes(n, ndim, extents_host) and bevf_dynamic_scatter_forward(...)
+ * The product of the extents (the coordinate bounding box) must be <= 2^34 cells.
+ */
+int bevf_dynamic_scatter_extents(const int *coors, int num_points, int ndim, int *extents_dev, void *stream);
+size_t bevf_dynamic_scatter_workspace_bytes(int num_points, int ndim, const int *extents_host);
+int bevf_dynamic_scatter_forward(const float *feats, const int *coors, int num_points, int num_features,
+                                 int ndim, const int *extents_host, int reduce_type, float *reduced_feats,
+                                 int *out_coors, int *coors_map, int *reduce_count, int *num_out_dev,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+/* grad_feats[N,C] is fully written (zero where no gradient flows).  workspace: M*C int32 for MAX. */
+int bevf_dynamic_scatter_backward(float *grad_feats, const float *grad_reduced_feats, const float *feats,
+                                  const float *reduced_feats, const int *coors_map, const int *reduce_count,
+                                  int num_points, int num_reduced, int num_features, int reduce_type,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ *
+ * bev_pool
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * bev_pool_forward  (ops/bev_pool/src/bev_pool.cpp:22-47 -> bev_pool_cuda.cu:20-42, launch :86-91;
+ * pybind name `bev_pool_forward`, bev_pool.cpp:90).  Argument order keeps the reference's
+ * (lengths before starts).
+ *   out[b,d,h,w,c]: for interval t with first row s = interval_starts[t], g = geom_feats[s,:] = (x,y,z,batch):
+ *   out[g3, g2, g0, g1, :] = sum_{i < interval_lengths[t]} x[s+i, :]
+ * Preconditions as in the reference: rows sorted so equal-rank rows are contiguous; all indices in range.
+ * `out` is fully written: cells no interval maps to are zero (the reference returns torch::zeros + K1).
+ * workspace: bevf_bev_pool_workspace_bytes(n, c).
+ */
+size_t bevf_bev_pool_workspace_bytes(int n, int c);
+int bevf_bev_pool_forward(const float *x, const int *geom_feats, const int *interval_lengths,
+                          const int *interval_starts, int n, int c, int n_intervals, int b, int d, int h, int w,
+                          float *out, void *workspace, size_t workspace_bytes, void *stream);
+/*
+ * bev_pool_backward  (bev_pool.cpp:60-87 -> bev_pool_cuda.cu:61-84, launch :93-97; pybind :92).
+ *   x_grad[s+i, :] = out_grad[g3, g2, g0, g1, :]; rows not covered by any interval are zero.
+ */
+int bevf_bev_pool_backward(const float *out_grad, const int *geom_feats, const int *interval_lengths,
+                           const int *interval_starts, int n, int c, int n_intervals, int b, int d, int h, int w,
+                           float *x_grad, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Fused view-transform pooling (the north-star form; replaces the tensor chain
+ * depth_lss.py:723-725 outer product -> :184-192 reshape / x[kept] / x[indices] -> bev_pool.py:146-172 ->
+ * depth_lss.py:202 collapse-Z, none of which is materialised):
+ *   out[b, c*nz + z, x, y] = sum over the interval's points p of depth[p] * ctx[pix(p), c]
+ * depth      [BN, D, fH, fW] fp32 (softmax output, frustum order: p = ((bn*D + d)*fH + h)*fW + w)
+ * ctx_nhwc   [BN, fH, fW, C] fp32 (context features, channels-last)
+ * src        [nk] int32: frustum index p of each kept point, sorted by rank (= kept.nonzero()[indices])
+ * interval_starts [n_int+1] int32 (CSR offsets into src; last = nk)
+ * interval_cell   [n_int] int32: (b*nz + z)*nx*ny + x*ny + y, strictly increasing
+ * out        [B, C*nz, nx, ny] fp32, fully written (zeros where no interval maps).
+ * C must be a multiple of 4 and <= 256.
+ */
+int bevf_bev_pool_fused_forward(const float *depth, const float *ctx_nhwc, const int *src,
+                                const int *interval_starts, const int *interval_cell, int n_intervals, int nk,
+                                int bn, int d, int fh, int fw, int c, int b, int nz, int nx, int ny, float *out,
+                                void *stream);
+/*
+ * Fused backward.  Given the output gradient in channels-last form out_grad_nhwc [B*nz*nx*ny, C]
+ * (row = (b*nz+z)*nx*ny + x*ny + y; bevf_nchw_to_nhwc(out_grad, ., B, C, nz*nx*ny) produces it from
+ * [B, C*nz, nx, ny]):
+ *   d_depth[p]      = sum_c out_grad[cell(p), c] * ctx[pix(p), c]      (0 for points not kept)
+ *   d_ctx[pix, c]   = sum over kept p at that pixel of depth[p] * out_grad[cell(p), c]
+ * cell_of_point [BN*D*fH*fW] int32: output row of each frustum point or -1.
+ * d_depth [BN,D,fH,fW], d_ctx_nhwc [BN,fH,fW,C] are fully written.
+ */
+int bevf_bev_pool_fused_backward(const float *out_grad_nhwc, const float *depth, const float *ctx_nhwc,
+                                 const int *cell_of_point, int bn, int d, int fh, int fw, int c, float *d_depth,
+                                 float *d_ctx_nhwc, void *stream);
+
+/* NCHW <-> NHWC transposes for the context features (tiny, tiled through shared memory). */
+int bevf_nchw_to_nhwc(const float *src, float *dst, int n, int c, int hw, void *stream);
+int bevf_nhwc_to_nchw(const float *src, float *dst, int n, int c, int hw, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVFRONT_B200_H_ */

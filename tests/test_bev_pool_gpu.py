@@ -1,0 +1,182 @@
+"""CUDA bev_pool (boundary + fused forms, through the C ABI) against the CPU oracle.
+Tolerance: 1e-5 relative (fp32; summation order differs from the reference, whose own argsort is unstable)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from bevfusion_3d_object_detection_b200 import ops, synthetic
+from bevfusion_3d_object_detection_b200.ops.bev_pool import bev_pool_ext
+from bevfusion_3d_object_detection_b200.ops.bev_pool.bev_pool import (QuickCumsum, QuickCumsumCuda,
+                                                                      QuickCumsumTrainingCuda)
+from bevfusion_3d_object_detection_b200.view_transform import BaseViewTransform
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _random_sorted_case(rng, n, c, B, D, H, W, max_run=60):
+    """rank-sorted rows with skewed interval lengths, reference rank formula (depth_lss.py:169)."""
+    cells = []
+    while sum(len(x) for x in cells) < n:
+        run = int(rng.integers(1, max_run)) if rng.random() < 0.9 else int(rng.integers(max_run, 12 * max_run))
+        cells.append(np.full(run, rng.integers(0, B * D * H * W)))
+    cell = np.concatenate(cells)[:n]
+    b, rem = cell // (D * H * W), cell % (D * H * W)
+    z, rem = rem // (H * W), rem % (H * W)
+    x, y = rem // W, rem % W
+    ranks = x * (W * D * B) + y * (D * B) + z * B + b
+    order = np.argsort(ranks, kind="stable")
+    geom = np.stack([x, y, z, b], 1)[order].astype(np.int32)
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    return feats, geom, ranks[order]
+
+
+@pytest.mark.parametrize("n,c,B,D,H,W", [(20000, 80, 1, 1, 60, 60), (50000, 80, 2, 2, 30, 40), (5000, 64, 1, 1, 16, 16),
+                                         (3000, 6, 1, 1, 8, 8), (7, 80, 1, 1, 4, 4), (40000, 256, 1, 1, 20, 20)])
+def test_boundary_forward_backward(oracle_mod, n, c, B, D, H, W):
+    rng = np.random.default_rng(n + c)
+    feats, geom, ranks = _random_sorted_case(rng, n, c, B, D, H, W)
+    x = torch.from_numpy(feats).cuda().requires_grad_(True)
+    out = ops.bev_pool(x, torch.from_numpy(geom).cuda().long(), torch.from_numpy(ranks).cuda(), B, D, H, W, True)
+    ref = oracle_mod.bev_pool(feats, geom, ranks, B, D, H, W)
+    assert out.shape == (B, c, D, H, W) and out.is_contiguous()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    og = rng.standard_normal(ref.shape).astype(np.float32)
+    out.backward(torch.from_numpy(og).cuda())
+    starts, lengths = oracle_mod.intervals_from_ranks(ranks)
+    want = oracle_mod.bev_pool_backward(np.ascontiguousarray(og.transpose(0, 2, 3, 4, 1)), geom, lengths, starts, B, D,
+                                        H, W)
+    np.testing.assert_array_equal(x.grad.cpu().numpy(), want)  # pure broadcast: exact
+    # inference branch: 0-dim tensor dims like self.nx[i] (depth_lss.py:199)
+    out2 = ops.bev_pool(x.detach(), torch.from_numpy(geom).cuda().long(), torch.from_numpy(ranks).cuda(), B,
+                        torch.tensor(D), torch.tensor(H), torch.nn.Parameter(torch.tensor(W), requires_grad=False), False)
+    np.testing.assert_array_equal(out2.cpu().numpy(), out.detach().cpu().numpy())  # deterministic kernel
+
+
+def test_ext_generic_path_for_non_tiling_intervals(oracle_mod):
+    """bev_pool_forward with (starts, lengths) that do NOT tile [0, n): the reference kernel only sums the rows
+    each interval names; rows outside every interval contribute nothing (and get zero gradient)."""
+    rng = np.random.default_rng(0)
+    n, c = 4000, 80
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    starts = np.arange(0, n, 100, dtype=np.int32)
+    lengths = rng.integers(1, 90, starts.shape[0]).astype(np.int32)  # gaps after every interval
+    geom = np.zeros((n, 4), np.int32)
+    geom[:, 0] = np.repeat(np.arange(starts.shape[0]), 100)[:n] // 8
+    geom[:, 1] = np.repeat(np.arange(starts.shape[0]), 100)[:n] % 8
+    args = [torch.from_numpy(a).cuda() for a in (geom, lengths, starts)]
+    out = bev_pool_ext.bev_pool_forward(torch.from_numpy(feats).cuda(), *args, 1, 1, 8, 8)
+    ref = oracle_mod.bev_pool_forward(feats, geom, lengths, starts, 1, 1, 8, 8)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    og = rng.standard_normal(ref.shape).astype(np.float32)
+    xg = bev_pool_ext.bev_pool_backward(torch.from_numpy(og).cuda(), *args, 1, 1, 8, 8)
+    np.testing.assert_array_equal(xg.cpu().numpy(), oracle_mod.bev_pool_backward(og, geom, lengths, starts, 1, 1, 8, 8))
+
+
+def test_ext_validates_inputs():
+    x = torch.zeros(8, 80, device="cuda")
+    g = torch.zeros(8, 4, dtype=torch.int32, device="cuda")
+    i = torch.zeros(1, dtype=torch.int32, device="cuda")
+    with pytest.raises(RuntimeError, match="int32"):
+        bev_pool_ext.bev_pool_forward(x, g.long(), i, i, 1, 1, 2, 2)
+    with pytest.raises(RuntimeError, match="float32"):
+        bev_pool_ext.bev_pool_forward(x.double(), g, i, i, 1, 1, 2, 2)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        bev_pool_ext.bev_pool_forward(x.t().contiguous().t(), g, i, i, 1, 1, 2, 2)
+    empty = bev_pool_ext.bev_pool_forward(x[:0], g[:0], i[:0], i[:0], 1, 1, 2, 2)
+    assert empty.shape == (1, 1, 2, 2, 80) and float(empty.abs().sum()) == 0.0
+    with pytest.raises(NotImplementedError):
+        QuickCumsumCuda.backward(None, None)
+
+
+def test_quick_cumsum_golden_on_gpu():
+    g = golden("quick_cumsum.npz")
+    pooled, pg = QuickCumsum.apply(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["geom"]).cuda(),
+                                   torch.from_numpy(g["ranks"]).cuda())
+    np.testing.assert_allclose(pooled.cpu().numpy(), g["pooled"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_array_equal(pg.cpu().numpy(), g["pooled_geom"])
+    out = QuickCumsumTrainingCuda.apply(torch.from_numpy(g["x"]).float().cuda(), torch.from_numpy(g["geom"]).cuda(),
+                                        torch.from_numpy(g["ranks"]).cuda(), 1, 1, 5, 8)
+    dense = np.zeros((1, 1, 5, 8, g["x"].shape[1]))
+    dense[0, 0, g["pooled_geom"][:, 0], g["pooled_geom"][:, 1]] = g["pooled"]
+    np.testing.assert_allclose(out.cpu().numpy(), dense, rtol=1e-5, atol=1e-5)
+
+
+def _view_case(batch, n_cams, feature_size, image_size, D_bound, C, xb, seed):
+    vt = BaseViewTransform(8, C, image_size, feature_size, xb, xb, [-10.0, 10.0, 20.0], D_bound).cuda()
+    rig = {k: torch.from_numpy(v).cuda() for k, v in synthetic.camera_rig(n_cams=n_cams, image_size=image_size,
+                                                                         batch=batch).items()}
+    geom = vt.get_geometry(**rig)
+    B, N, D, fH, fW, _ = geom.shape
+    depth, ctx = synthetic.camera_features(n_cams=N, D=D, C=C, feature_size=feature_size, batch=B, seed=seed)
+    return vt, geom, depth, ctx
+
+
+@pytest.mark.parametrize("case", ["small_b2", "config_A"])
+def test_fused_forward_matches_reference_chain(oracle_mod, case):
+    if case == "small_b2":
+        vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 1)
+    else:  # BASELINE configs[0]/[1]: 6 cams x 118 x 32 x 88 x 80 ch -> 360 x 360
+        vt, geom, depth, ctx = _view_case(1, 6, (32, 88), (256, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 0)
+    B, N, D, fH, fW, _ = geom.shape
+    C = ctx.shape[1]
+    d_t, c_t = torch.from_numpy(depth).cuda(), torch.from_numpy(ctx).cuda()
+    tabs = vt.build_tables(geom)
+    out = vt.pool_fused(d_t, c_t)
+    # (1) against the boundary form fed with the materialised frustum tensor (the reference's own data path)
+    x = (d_t.unsqueeze(1) * c_t.unsqueeze(2)).view(B, N, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    vt.eval()
+    ref_gpu = vt.bev_pool(x, geom)
+    assert out.shape == ref_gpu.shape == (B, C * int(vt.nx[2]), int(vt.nx[0]), int(vt.nx[1]))
+    scale = float(ref_gpu.abs().max())
+    np.testing.assert_allclose(out.cpu().numpy(), ref_gpu.cpu().numpy(), rtol=RTOL, atol=RTOL * scale)
+    # (2) against the CPU oracle of the whole chain
+    gf, kept, ranks, indices = vt.bev_pool_aux(geom)
+    src = torch.nonzero(kept, as_tuple=False).squeeze(1)[indices].cpu().numpy()
+    starts, lengths = oracle_mod.intervals_from_ranks(ranks.cpu().numpy())
+    want = oracle_mod.bev_pool_fused(depth, ctx, src, gf.int().cpu().numpy(), starts, lengths, B, int(vt.nx[2]),
+                                     int(vt.nx[0]), int(vt.nx[1]))
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=RTOL, atol=RTOL * scale)
+    if case == "config_A":
+        assert tabs.nk > 1_700_000 and 40_000 < tabs.n_intervals < 50_000
+
+
+def test_fused_backward_matches_autograd_of_reference_chain():
+    vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 2)
+    B, N, D, fH, fW, _ = geom.shape
+    C = ctx.shape[1]
+    vt.build_tables(geom)
+    d1 = torch.from_numpy(depth).cuda().requires_grad_(True)
+    c1 = torch.from_numpy(ctx).cuda().requires_grad_(True)
+    out = vt.pool_fused(d1, c1)
+    g = torch.randn_like(out)
+    out.backward(g)
+    # reference chain with torch autograd through the boundary op (QuickCumsumTrainingCuda backward = K2)
+    d2 = torch.from_numpy(depth).cuda().requires_grad_(True)
+    c2 = torch.from_numpy(ctx).cuda().requires_grad_(True)
+    x = (d2.unsqueeze(1) * c2.unsqueeze(2)).view(B, N, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    vt.train()
+    ref = vt.bev_pool(x, geom)
+    ref.backward(g)
+    for a, b in ((d1.grad, d2.grad), (c1.grad, c2.grad)):
+        scale = float(b.abs().max())
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+
+
+def test_linearity_and_zero_cells_full_size():
+    """Size-independent properties at BASELINE's full size: pool(a*d, c) == a*pool(d, c); cells no frustum point
+    reaches are exactly zero; the sum over the BEV grid equals the sum of depth*ctx over kept points."""
+    vt, geom, depth, ctx = _view_case(1, 6, (32, 88), (256, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 3)
+    d_t, c_t = torch.from_numpy(depth).cuda(), torch.from_numpy(ctx).cuda()
+    tabs = vt.build_tables(geom)
+    out = vt.pool_fused(d_t, c_t)
+    out2 = vt.pool_fused(d_t * 2.0, c_t)
+    np.testing.assert_allclose(out2.cpu().numpy(), 2.0 * out.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    occ = torch.zeros(360 * 360, dtype=torch.bool, device="cuda")
+    occ[tabs.interval_cell.long()] = True
+    assert float(out.view(80, -1)[:, ~occ].abs().max()) == 0.0
+    kept_w = torch.zeros(depth.size, device="cuda", dtype=torch.float64)
+    kept_w[tabs.src.long()] = 1.0
+    total = ((d_t.double() * kept_w.view_as(d_t)).sum(1, keepdim=True) * c_t.double()).sum()
+    np.testing.assert_allclose(float(out.double().sum()), float(total), rtol=1e-6)

@@ -1,0 +1,90 @@
+"""Host-side mirror of the reference interface: attributes, geometry, table construction, error behaviour.
+CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from bevfusion_3d_object_detection_b200 import ops, synthetic
+from bevfusion_3d_object_detection_b200.view_transform import BaseViewTransform, gen_dx_bx
+
+
+def test_voxelization_module_surface():
+    v = ops.Voxelization([0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, (120000, 160000))
+    assert v.max_voxels == (120000, 160000) and v.deterministic is True
+    assert v.grid_size.tolist() == [1440, 1440, 40]
+    assert [int(x) for x in v.pcd_shape] == [1440, 1440, 1]
+    assert "max_voxels=(120000, 160000)" in repr(v) and repr(v).startswith("Voxelization(")
+    assert ops.Voxelization([1, 1, 1], [0, 0, 0, 4, 4, 4], 5, 300).max_voxels == (300, 300)
+    assert len(list(v.parameters())) == 0
+
+
+def test_cpu_tensors_fail_loudly():
+    v = ops.Voxelization([1, 1, 1], [0, 0, 0, 4, 4, 4], 5, 300)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        v(torch.zeros(10, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.dynamic_scatter(torch.zeros(10, 4), torch.zeros(10, 3, dtype=torch.int32), "max")
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.bev_pool(torch.zeros(4, 8), torch.zeros(4, 4, dtype=torch.int32), torch.zeros(4, dtype=torch.long), 1, 1,
+                     2, 2, False)
+    with pytest.raises(AssertionError):
+        ops.bev_pool(torch.zeros(4, 8), torch.zeros(3, 4, dtype=torch.int32), torch.zeros(4), 1, 1, 2, 2, True)
+
+
+def test_gen_dx_bx():
+    dx, bx, nx = gen_dx_bx([-54.0, 54.0, 0.3], [-54.0, 54.0, 0.3], [-10.0, 10.0, 20.0])
+    assert nx.tolist() == [360, 360, 1]
+    np.testing.assert_allclose(dx.numpy(), [0.3, 0.3, 20.0])
+    np.testing.assert_allclose(bx.numpy(), [-53.85, -53.85, 0.0], rtol=1e-6)
+
+
+def _small_vt():
+    return BaseViewTransform(8, 6, (64, 96), (4, 6), [-12.0, 12.0, 0.75], [-12.0, 12.0, 0.75], [-10.0, 10.0, 20.0],
+                             [1.0, 15.0, 1.0])
+
+
+def test_geometry_and_aux_match_reference_golden():
+    g = golden("view_geometry.npz")
+    vt = _small_vt()
+    np.testing.assert_array_equal(vt.frustum.detach().numpy(), g["frustum"])
+    rig = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("rig_")}
+    geom = vt.get_geometry(**rig, extra_rots=torch.from_numpy(g["extra_rots"]),
+                           extra_trans=torch.from_numpy(g["extra_trans"]))
+    np.testing.assert_array_equal(geom.numpy(), g["geom"])  # same torch ops on the same CPU: bit-equal
+    gf, kept, ranks, indices = vt.bev_pool_aux(geom)
+    np.testing.assert_array_equal(kept.numpy(), g["kept"])
+    np.testing.assert_array_equal(ranks.numpy(), g["ranks"])
+    np.testing.assert_array_equal(gf.numpy(), g["geom_feats"])
+
+
+def test_fused_tables_describe_the_same_pooling(oracle_mod):
+    """BevPoolTables (src / CSR starts / cells / cell_of_point) reproduce, through the fused oracle, what the
+    reference chain (outer product -> x[kept] -> x[indices] -> bev_pool -> collapse Z) computes."""
+    vt = _small_vt()
+    rig = {k: torch.from_numpy(v) for k, v in synthetic.camera_rig(n_cams=3, image_size=(64, 96), batch=2,
+                                                                  src_size=(200, 300), resize=0.4).items()}
+    geom = vt.get_geometry(**rig)
+    B, N, D, fH, fW, _ = geom.shape
+    C = 8
+    depth, ctx = synthetic.camera_features(n_cams=N, D=D, C=C, feature_size=(fH, fW), batch=B, seed=4)
+    gf, kept, ranks, indices = vt.bev_pool_aux(geom)
+    # reference chain on CPU (oracle restatement of K1)
+    x = torch.from_numpy(depth).unsqueeze(1) * torch.from_numpy(ctx).unsqueeze(2)       # [BN, C, D, fH, fW]
+    x = x.view(B, N, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2).reshape(-1, C)[kept][indices]
+    ref = oracle_mod.bev_pool(x.numpy(), gf.numpy(), ranks.numpy(), B, int(vt.nx[2]), int(vt.nx[0]), int(vt.nx[1]))
+    ref = np.concatenate([ref[:, :, z] for z in range(ref.shape[2])], 1)
+    tabs = ops.BevPoolTables(gf, kept, ranks, indices, B, int(vt.nx[2]), int(vt.nx[0]), int(vt.nx[1]))
+    assert tabs.interval_starts[-1].item() == tabs.nk == int(kept.sum())
+    assert (tabs.interval_cell[1:] > tabs.interval_cell[:-1]).all()
+    starts = tabs.interval_starts[:-1].numpy()
+    lengths = np.diff(tabs.interval_starts.numpy())
+    cell = tabs.interval_cell.long()
+    nz, nx, ny = tabs.nz, tabs.nx, tabs.ny
+    geom4 = torch.stack([(cell // ny) % nx, cell % ny, (cell // (nx * ny)) % nz, cell // (nz * nx * ny)], 1)
+    geom4_rows = np.zeros((tabs.nk, 4), np.int32)
+    geom4_rows[starts] = geom4.numpy()
+    got = oracle_mod.bev_pool_fused(depth, ctx, tabs.src.numpy(), geom4_rows, starts, lengths, B, nz, nx, ny)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    cop = tabs.cell_of_point.numpy()
+    assert (cop >= 0).sum() == tabs.nk and (cop[~kept.numpy()] == -1).all()
