@@ -10,13 +10,10 @@
 //   K3 emit        out_coors[rank] = decode(key)
 //   K4 reduce      coors_map, reduce_count, feature reduction with native float atomics
 //                  (max uses the ordered-int trick instead of a CAS loop)
+#include "bitmap_rank.cuh"
 #include "common.cuh"
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kItems = 4;
-constexpr int kTile = kThreads * kItems;
 
 struct Extents {
   int e[4];
@@ -63,120 +60,17 @@ __global__ void mark_kernel(const int *__restrict__ coors, int n, Extents E, uns
   atomicOr(bitmap + (key >> 5), 1u << (unsigned)(key & 31));
 }
 
-__global__ void __launch_bounds__(kThreads)
-    popc_count_kernel(const unsigned *__restrict__ bitmap, long long nwords, int *__restrict__ block_counts) {
-  __shared__ int ws[kThreads / 32];
-  long long base = (long long)blockIdx.x * kTile;
-  int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    long long w = base + (long long)k * kThreads + threadIdx.x;
-    if (w < nwords) cnt += __popc(bitmap[w]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < kThreads / 32; ++w) t += ws[w];
-    block_counts[blockIdx.x] = t;
-  }
-}
-
-// exclusive prefix of block_counts, in place (single block; nblk is small: words / 1024)
-__global__ void __launch_bounds__(1024) block_scan_kernel(int *__restrict__ block_counts, int nblk,
-                                                           int *__restrict__ total) {
-  __shared__ int ws[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nblk; base += 1024) {
-    int i = base + threadIdx.x;
-    int v = (i < nblk) ? block_counts[i] : 0;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((int)(threadIdx.x & 31) >= o) inc += u;
-    }
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int w = ws[threadIdx.x];
-      int winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, winc, o);
-        if ((int)threadIdx.x >= o) winc += u;
-      }
-      ws[threadIdx.x] = winc - w;
-    }
-    __syncthreads();
-    int excl = carry + ws[threadIdx.x >> 5] + inc - v;
-    if (i < nblk) block_counts[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-
-// word_prefix[w] = number of set bits in words < w; also emits out_coors for the bits of each word
-__global__ void __launch_bounds__(kThreads)
-    popc_scan_emit_kernel(const unsigned *__restrict__ bitmap, long long nwords,
-                          const int *__restrict__ block_offsets, int *__restrict__ word_prefix, Extents E,
-                          int *__restrict__ out_coors) {
-  __shared__ int ws[kThreads / 32];
-  const long long base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * kItems;
-  unsigned wv[kItems];
-  int local = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    long long w = base + k;
-    wv[k] = (w < nwords) ? bitmap[w] : 0u;
-    local += __popc(wv[k]);
-  }
-  int inc = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int u = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((int)(threadIdx.x & 31) >= o) inc += u;
-  }
-  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    int w = (threadIdx.x < kThreads / 32) ? ws[threadIdx.x] : 0;
-    int winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, winc, o);
-      if ((int)threadIdx.x >= o) winc += u;
-    }
-    if (threadIdx.x < kThreads / 32) ws[threadIdx.x] = winc - w;
-  }
-  __syncthreads();
-  int run = block_offsets[blockIdx.x] + ws[threadIdx.x >> 5] + inc - local;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    long long w = base + k;
-    if (w < nwords) {
-      word_prefix[w] = run;
-      unsigned bits = wv[k];
-      while (bits) {
-        int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        unsigned long long key = ((unsigned long long)w << 5) | (unsigned)b;
-        int *o = out_coors + (size_t)run * E.ndim;
-        for (int j = E.ndim - 1; j >= 0; --j) {
-          o[j] = (int)(key % (unsigned long long)E.e[j]);
-          key /= (unsigned long long)E.e[j];
-        }
-        run += 1;
-      }
+struct EmitCoors {
+  Extents E;
+  int *out_coors;
+  __device__ void operator()(int rank, unsigned long long key) const {
+    int *o = out_coors + (size_t)rank * E.ndim;
+    for (int j = E.ndim - 1; j >= 0; --j) {
+      o[j] = (int)(key % (unsigned long long)E.e[j]);
+      key /= (unsigned long long)E.e[j];
     }
   }
-}
+};
 
 __device__ __forceinline__ void atomic_max_float(float *addr, float val) {
   if (val >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(val));
@@ -295,8 +189,7 @@ int key_space(const int *ext, int ndim, long long &nwords) {
 size_t carve_scatter(ScatterWs &w, void *ws, size_t bytes, long long nwords) {
   bevf::Workspace a(ws, bytes);
   w.nwords = nwords;
-  w.nblk = (int)((nwords + kTile - 1) / kTile);
-  if (w.nblk < 1) w.nblk = 1;
+  w.nblk = bevf::rank_num_blocks(nwords);
   w.bitmap = a.take<unsigned>((size_t)nwords);
   w.word_prefix = a.take<int>((size_t)nwords);
   w.block_counts = a.take<int>((size_t)w.nblk);
@@ -351,12 +244,8 @@ BEVF_API int bevf_dynamic_scatter_forward(const float *feats, const int *coors, 
   BEVF_CHECK_CUDA(cudaMemsetAsync(w.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
   mark_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(coors, n, E, w.bitmap);
   BEVF_CHECK_LAUNCH();
-  popc_count_kernel<<<w.nblk, kThreads, 0, st>>>(w.bitmap, nwords, w.block_counts);
-  BEVF_CHECK_LAUNCH();
-  block_scan_kernel<<<1, 1024, 0, st>>>(w.block_counts, w.nblk, num_out_dev);
-  BEVF_CHECK_LAUNCH();
-  popc_scan_emit_kernel<<<w.nblk, kThreads, 0, st>>>(w.bitmap, nwords, w.block_counts, w.word_prefix, E, out_coors);
-  BEVF_CHECK_LAUNCH();
+  rc = bevf::rank_build(w.bitmap, nwords, w.word_prefix, w.block_counts, num_out_dev, EmitCoors{E, out_coors}, st);
+  if (rc) return rc;
   const float init = (reduce_type == BEVF_REDUCE_MAX) ? -__builtin_inff() : 0.f;
   init_reduce_kernel<<<bevf::kNumSMs * 4, 256, 0, st>>>(reduced, reduce_count, (size_t)n, c, init);
   BEVF_CHECK_LAUNCH();

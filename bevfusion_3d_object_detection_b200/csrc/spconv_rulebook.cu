@@ -1,0 +1,389 @@
+// spconv_rulebook.cu -- coordinate index + rulebook (indice-pair) generation for sparse 3-D convolution.
+//
+// Restates what spconv>=2.3's SpconvOps.get_indice_pairs_implicit_gemm produces (call site in the reference:
+// projects/SparseConvolution/sparse_functional.py:118-137): pair_fwd[kv, n_out] (input row feeding output j
+// under kernel tap k, -1 = none).  spconv builds it with a hash table (+ thrust sort for the output order);
+// here the lookup structure is an occupancy bitmap over the (batch, X, Y, Z) grid with a popcount prefix
+// (bitmap_rank.cuh):
+//   * coordinate -> row lookup is one 4-byte bitmap read for a miss (most of the 27 taps miss) and two more
+//     reads for a hit; no probing loops, no atomicCAS;
+//   * the output sites of a strided convolution fall out of the same scan already sorted by linear index,
+//     which is this framework's canonical output order (SURVEY 7 "Rulebook bit-exact");
+//   * a level produced by a strided conv needs no row permutation (row == rank), only the raw voxelizer
+//     output (first-appearance order) does.
+#include "bitmap_rank.cuh"
+#include "common.cuh"
+
+namespace {
+
+struct Grid {
+  int b, x, y, z;
+};
+
+struct IndexView {
+  const unsigned *bitmap;
+  const int *word_prefix;
+  const int *perm;  // rank -> row, or nullptr when rows are already in ascending linear order
+  Grid g;
+};
+
+struct ConvGeom {
+  int k[3], s[3], p[3], d[3];
+};
+
+__device__ __forceinline__ long long lin_cell(const Grid &g, int b, int x, int y, int z) {
+  return (((long long)b * g.x + x) * g.y + y) * g.z + z;
+}
+
+__device__ __forceinline__ int index_lookup(const IndexView &ix, int b, int x, int y, int z) {
+  if ((unsigned)x >= (unsigned)ix.g.x || (unsigned)y >= (unsigned)ix.g.y || (unsigned)z >= (unsigned)ix.g.z) return -1;
+  const long long cell = lin_cell(ix.g, b, x, y, z);
+  const unsigned bits = __ldg(ix.bitmap + (cell >> 5));
+  const unsigned bit = (unsigned)(cell & 31);
+  if (!((bits >> bit) & 1u)) return -1;
+  const int rank = __ldg(ix.word_prefix + (cell >> 5)) + __popc(bits & ((1u << bit) - 1u));
+  return ix.perm ? __ldg(ix.perm + rank) : rank;
+}
+
+__global__ void mark_sites_kernel(const int *__restrict__ indices, int n, Grid g, unsigned *__restrict__ bitmap,
+                                  int *__restrict__ error_flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);  // (b, x, y, z)
+  if ((unsigned)c.x >= (unsigned)g.b || (unsigned)c.y >= (unsigned)g.x || (unsigned)c.z >= (unsigned)g.y ||
+      (unsigned)c.w >= (unsigned)g.z) {
+    *error_flag = 1;
+    return;
+  }
+  long long cell = lin_cell(g, c.x, c.y, c.z, c.w);
+  unsigned old = atomicOr(bitmap + (cell >> 5), 1u << (unsigned)(cell & 31));
+  if ((old >> (unsigned)(cell & 31)) & 1u) *error_flag = 2;  // duplicate coordinate
+}
+
+struct EmitNothing {
+  __device__ void operator()(int, unsigned long long) const {}
+};
+
+__global__ void fill_perm_kernel(const int *__restrict__ indices, int n, Grid g, const unsigned *__restrict__ bitmap,
+                                 const int *__restrict__ word_prefix, int *__restrict__ perm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+  if ((unsigned)c.x >= (unsigned)g.b || (unsigned)c.y >= (unsigned)g.x || (unsigned)c.z >= (unsigned)g.y ||
+      (unsigned)c.w >= (unsigned)g.z)
+    return;
+  long long cell = lin_cell(g, c.x, c.y, c.z, c.w);
+  unsigned bits = bitmap[cell >> 5];
+  int rank = word_prefix[cell >> 5] + __popc(bits & ((1u << (unsigned)(cell & 31)) - 1u));
+  perm[rank] = i;
+}
+
+// SubM: out sites == in sites; kernel centred; one thread per (site, tap-x/y column), 3..k[2] z-taps share the
+// bitmap word most of the time.
+__global__ void __launch_bounds__(256)
+    subm_rulebook_kernel(const int *__restrict__ indices, int n, IndexView ix, ConvGeom cg, int ld,
+                         int *__restrict__ pair_fwd) {
+  const int kxy = cg.k[0] * cg.k[1];
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * kxy) return;
+  const int j = (int)(t % n);  // consecutive threads -> consecutive sites: coalesced pair_fwd stores
+  const int col = (int)(t / n);
+  const int kx = col / cg.k[1], ky = col % cg.k[1];
+  const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + j);
+  const int x = c.y + (kx - cg.k[0] / 2) * cg.d[0];
+  const int y = c.z + (ky - cg.k[1] / 2) * cg.d[1];
+  for (int kz = 0; kz < cg.k[2]; ++kz) {
+    const int z = c.w + (kz - cg.k[2] / 2) * cg.d[2];
+    const int tap = col * cg.k[2] + kz;
+    pair_fwd[(size_t)tap * ld + j] = index_lookup(ix, c.x, x, y, z);
+  }
+}
+
+// strided conv, pass 1: every input marks the output sites it reaches
+__global__ void __launch_bounds__(256)
+    strided_mark_kernel(const int *__restrict__ indices, int n, ConvGeom cg, Grid og, unsigned *__restrict__ out_bitmap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+  for (int kx = 0; kx < cg.k[0]; ++kx) {
+    int ox = c.y + cg.p[0] - kx * cg.d[0];
+    if (ox < 0 || ox % cg.s[0]) continue;
+    ox /= cg.s[0];
+    if (ox >= og.x) continue;
+    for (int ky = 0; ky < cg.k[1]; ++ky) {
+      int oy = c.z + cg.p[1] - ky * cg.d[1];
+      if (oy < 0 || oy % cg.s[1]) continue;
+      oy /= cg.s[1];
+      if (oy >= og.y) continue;
+      for (int kz = 0; kz < cg.k[2]; ++kz) {
+        int oz = c.w + cg.p[2] - kz * cg.d[2];
+        if (oz < 0 || oz % cg.s[2]) continue;
+        oz /= cg.s[2];
+        if (oz >= og.z) continue;
+        long long cell = lin_cell(og, c.x, ox, oy, oz);
+        unsigned m = 1u << (unsigned)(cell & 31);
+        if (!(out_bitmap[cell >> 5] & m)) atomicOr(out_bitmap + (cell >> 5), m);
+      }
+    }
+  }
+}
+
+struct EmitSites {
+  Grid og;
+  int *out_indices;
+  int cap;
+  __device__ void operator()(int rank, unsigned long long key) const {
+    if (rank >= cap) return;
+    int4 o;
+    o.w = (int)(key % (unsigned)og.z); key /= (unsigned)og.z;
+    o.z = (int)(key % (unsigned)og.y); key /= (unsigned)og.y;
+    o.y = (int)(key % (unsigned)og.x); key /= (unsigned)og.x;
+    o.x = (int)key;
+    reinterpret_cast<int4 *>(out_indices)[rank] = o;
+  }
+};
+
+// strided conv, pass 2: for every output site and tap, look the input up
+__global__ void __launch_bounds__(256)
+    strided_rulebook_kernel(const int *__restrict__ out_indices, const int *__restrict__ n_out_dev, int n_out_host,
+                            IndexView ix, ConvGeom cg, int ld, int *__restrict__ pair_fwd) {
+  const int n_out = n_out_dev ? min(*n_out_dev, ld) : n_out_host;
+  const int kxy = cg.k[0] * cg.k[1];
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)ld * kxy) return;
+  const int j = (int)(t % ld);
+  if (j >= n_out) return;
+  const int col = (int)(t / ld);
+  const int kx = col / cg.k[1], ky = col % cg.k[1];
+  const int4 o = __ldg(reinterpret_cast<const int4 *>(out_indices) + j);
+  const int x = o.y * cg.s[0] - cg.p[0] + kx * cg.d[0];
+  const int y = o.z * cg.s[1] - cg.p[1] + ky * cg.d[1];
+  for (int kz = 0; kz < cg.k[2]; ++kz) {
+    const int z = o.w * cg.s[2] - cg.p[2] + kz * cg.d[2];
+    const int tap = col * cg.k[2] + kz;
+    pair_fwd[(size_t)tap * ld + j] = index_lookup(ix, o.x, x, y, z);
+  }
+}
+
+// SparseConvTensor.dense(): [B, C, X, Y, Z]; one thread per (site, channel), channel fastest in the read
+__global__ void __launch_bounds__(256)
+    to_dense_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n, int c, Grid g,
+                    float *__restrict__ dense) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * c) return;
+  const int i = (int)(t / c), ch = (int)(t % c);
+  const int4 q = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+  const size_t vol = (size_t)g.x * g.y * g.z;
+  dense[((size_t)q.x * c + ch) * vol + ((size_t)q.y * g.y + q.z) * g.z + q.w] = feats[t];
+}
+
+// BEVFusionSparseEncoder tail (sparse_encoder.py:147-151): dense() [N,C,X,Y,Z] -> permute(0,1,4,2,3) ->
+// view(N, C*Z, X, Y), fused: bev[b, ch*Z + z, x, y]
+__global__ void __launch_bounds__(256)
+    to_bev_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n, int c, Grid g,
+                  float *__restrict__ bev) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * c) return;
+  const int i = (int)(t / c), ch = (int)(t % c);
+  const int4 q = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+  bev[((((size_t)q.x * c + ch) * g.z + q.w) * g.x + q.y) * g.y + q.z] = feats[t];
+}
+
+struct IndexMem {
+  unsigned *bitmap;
+  int *word_prefix;
+  int *block_counts;
+  int *scalars;  // [0] total, [1] error flag
+  long long nwords;
+};
+
+int grid_words(int batch, const int *shape, long long &nwords) {
+  BEVF_CHECK_ARG(batch > 0 && shape[0] > 0 && shape[1] > 0 && shape[2] > 0, "bad grid %d x (%d,%d,%d)", batch,
+                 shape[0], shape[1], shape[2]);
+  long long cells = (long long)batch * shape[0] * shape[1] * shape[2];
+  if (cells >= (1ll << 36)) {
+    bevf::set_error("sparse grid with %lld cells is not supported (limit 2^36)", cells);
+    return BEVF_ERR_UNSUPPORTED;
+  }
+  nwords = (cells + 31) / 32;
+  return BEVF_OK;
+}
+
+size_t carve_index(IndexMem &m, void *mem, size_t bytes, long long nwords) {
+  bevf::Workspace a(mem, bytes);
+  m.nwords = nwords;
+  m.scalars = a.take<int>(64);
+  m.bitmap = a.take<unsigned>((size_t)nwords);
+  m.word_prefix = a.take<int>((size_t)nwords);
+  m.block_counts = a.take<int>((size_t)bevf::rank_num_blocks(nwords));
+  return a.off;
+}
+
+void fill_geom(ConvGeom &cg, const int *k, const int *s, const int *p, const int *d) {
+  for (int j = 0; j < 3; ++j) {
+    cg.k[j] = k[j];
+    cg.s[j] = s ? s[j] : 1;
+    cg.p[j] = p ? p[j] : 0;
+    cg.d[j] = d ? d[j] : 1;
+  }
+}
+
+int check_geom(const int *k, const int *s, const int *p, const int *d) {
+  for (int j = 0; j < 3; ++j) {
+    BEVF_CHECK_ARG(k[j] >= 1 && k[j] <= 7, "kernel size %d out of range 1..7", k[j]);
+    BEVF_CHECK_ARG(!s || s[j] >= 1, "stride must be >= 1");
+    BEVF_CHECK_ARG(!p || p[j] >= 0, "padding must be >= 0");
+    BEVF_CHECK_ARG(!d || d[j] >= 1, "dilation must be >= 1");
+  }
+  return BEVF_OK;
+}
+
+}  // namespace
+
+BEVF_API int bevf_spconv_out_shape(const int *shape, const int *k, const int *s, const int *p, const int *d,
+                                   int *out_shape) {
+  for (int j = 0; j < 3; ++j) out_shape[j] = (shape[j] + 2 * p[j] - d[j] * (k[j] - 1) - 1) / s[j] + 1;
+  return BEVF_OK;
+}
+
+BEVF_API size_t bevf_spconv_index_bytes(int batch, const int *shape) {
+  long long nwords;
+  if (grid_words(batch, shape, nwords)) return 0;
+  IndexMem m;
+  return carve_index(m, nullptr, 0, nwords) + 256;
+}
+
+BEVF_API int bevf_spconv_index_build(const int *indices, int n, int batch, const int *shape, void *index_mem,
+                                     size_t index_bytes, int *perm, void *stream) {
+  long long nwords;
+  int rc = grid_words(batch, shape, nwords);
+  if (rc) return rc;
+  IndexMem m;
+  size_t need = carve_index(m, index_mem, index_bytes, nwords);
+  if (!index_mem || need > index_bytes) {
+    bevf::set_error("spconv index memory too small: need %zu bytes, got %zu", need, index_bytes);
+    return BEVF_ERR_WORKSPACE;
+  }
+  BEVF_CHECK_ARG(n >= 0 && (n == 0 || indices), "bad indices");
+  BEVF_CHECK_ARG((reinterpret_cast<uintptr_t>(indices) & 15u) == 0, "indices must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g{batch, shape[0], shape[1], shape[2]};
+  BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
+  BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
+  if (n > 0) {
+    mark_sites_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, g, m.bitmap, m.scalars + 1);
+    BEVF_CHECK_LAUNCH();
+  }
+  rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitNothing{}, st);
+  if (rc) return rc;
+  if (perm && n > 0) {
+    fill_perm_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, g, m.bitmap, m.word_prefix, perm);
+    BEVF_CHECK_LAUNCH();
+  }
+  return BEVF_OK;
+}
+
+// error flag of the last index build: 0 ok, 1 coordinate out of the grid, 2 duplicate coordinate (device int)
+BEVF_API const int *bevf_spconv_index_error_flag(void *index_mem, size_t index_bytes, int batch, const int *shape) {
+  long long nwords;
+  if (grid_words(batch, shape, nwords)) return nullptr;
+  IndexMem m;
+  carve_index(m, index_mem, index_bytes, nwords);
+  return m.scalars + 1;
+}
+
+BEVF_API int bevf_spconv_subm_rulebook(const int *indices, int n, int batch, const int *shape, const int *ksize,
+                                       const int *dilation, const void *index_mem, size_t index_bytes,
+                                       const int *perm, int *pair_fwd, int ld, void *stream) {
+  int rc = check_geom(ksize, nullptr, nullptr, dilation);
+  if (rc) return rc;
+  long long nwords;
+  rc = grid_words(batch, shape, nwords);
+  if (rc) return rc;
+  BEVF_CHECK_ARG(ld >= n, "pair_fwd leading dimension %d < n %d", ld, n);
+  if (n == 0) return BEVF_OK;
+  IndexMem m;
+  carve_index(m, const_cast<void *>(index_mem), index_bytes, nwords);
+  IndexView ix{m.bitmap, m.word_prefix, perm, Grid{batch, shape[0], shape[1], shape[2]}};
+  ConvGeom cg;
+  fill_geom(cg, ksize, nullptr, nullptr, dilation);
+  long long threads = (long long)n * ksize[0] * ksize[1];
+  subm_rulebook_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, ix, cg, ld,
+                                                                                        pair_fwd);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, int batch, const int *in_shape,
+                                       const int *ksize, const int *stride, const int *padding, const int *dilation,
+                                       void *out_index_mem, size_t out_index_bytes, int *out_indices, int cap,
+                                       int *n_out_dev, void *stream) {
+  int rc = check_geom(ksize, stride, padding, dilation);
+  if (rc) return rc;
+  int os[3];
+  bevf_spconv_out_shape(in_shape, ksize, stride, padding, dilation, os);
+  long long nwords;
+  rc = grid_words(batch, os, nwords);
+  if (rc) return rc;
+  IndexMem m;
+  size_t need = carve_index(m, out_index_mem, out_index_bytes, nwords);
+  if (!out_index_mem || need > out_index_bytes) {
+    bevf::set_error("spconv output index memory too small: need %zu bytes, got %zu", need, out_index_bytes);
+    return BEVF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid og{batch, os[0], os[1], os[2]};
+  ConvGeom cg;
+  fill_geom(cg, ksize, stride, padding, dilation);
+  BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
+  BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
+  if (n_in > 0) {
+    strided_mark_kernel<<<bevf::ceil_div(n_in, 256), 256, 0, st>>>(in_indices, n_in, cg, og, m.bitmap);
+    BEVF_CHECK_LAUNCH();
+  }
+  rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitSites{og, out_indices, cap},
+                        st);
+  if (rc) return rc;
+  if (n_out_dev)
+    BEVF_CHECK_CUDA(cudaMemcpyAsync(n_out_dev, m.scalars, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, const int *n_out_dev, int batch,
+                                          const int *in_shape, const int *ksize, const int *stride,
+                                          const int *padding, const int *dilation, const void *in_index_mem,
+                                          size_t in_index_bytes, const int *in_perm, int *pair_fwd, int ld,
+                                          void *stream) {
+  int rc = check_geom(ksize, stride, padding, dilation);
+  if (rc) return rc;
+  long long nwords;
+  rc = grid_words(batch, in_shape, nwords);
+  if (rc) return rc;
+  BEVF_CHECK_ARG(ld >= n_out, "pair_fwd leading dimension %d < n_out %d", ld, n_out);
+  if (ld == 0) return BEVF_OK;
+  IndexMem m;
+  carve_index(m, const_cast<void *>(in_index_mem), in_index_bytes, nwords);
+  IndexView ix{m.bitmap, m.word_prefix, in_perm, Grid{batch, in_shape[0], in_shape[1], in_shape[2]}};
+  ConvGeom cg;
+  fill_geom(cg, ksize, stride, padding, dilation);
+  long long threads = (long long)ld * ksize[0] * ksize[1];
+  strided_rulebook_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(out_indices, n_out_dev,
+                                                                                           n_out, ix, cg, ld, pair_fwd);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_sparse_to_dense(const float *feats, const int *indices, int n, int c, int batch, const int *shape,
+                                  float *dense, int bev_layout, void *stream) {
+  BEVF_CHECK_ARG(batch > 0 && c > 0 && n >= 0, "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t total = (size_t)batch * c * shape[0] * shape[1] * shape[2];
+  BEVF_CHECK_CUDA(cudaMemsetAsync(dense, 0, total * sizeof(float), st));
+  if (n == 0) return BEVF_OK;
+  Grid g{batch, shape[0], shape[1], shape[2]};
+  long long threads = (long long)n * c;
+  if (bev_layout) to_bev_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, c, g, dense);
+  else to_dense_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, c, g, dense);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}

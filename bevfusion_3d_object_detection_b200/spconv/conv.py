@@ -1,0 +1,217 @@
+"""SubMConv3d / SparseConv3d with the spconv-2.x constructor and parameter layout
+(`SparseConvolution.__init__`, mirrored by the reference at projects/SparseConvolution/sparse_conv.py:288-360;
+registered into mmengine MODELS under the same names as mmdet3d/models/layers/spconv/overwrite_spconv/
+write_spconv2.py:21-38 does for the spconv classes).
+"""
+import math
+import os
+
+import torch
+from torch import nn
+
+from . import functional as Fsp
+from .core import SparseConvTensor
+from .modules import SparseModule
+
+_DEFAULT_PRECISION = os.environ.get("BEVFRONT_SPCONV_PRECISION", "fp32")
+
+
+def set_default_precision(precision):
+    """'fp32' (FFMA, 1e-5 parity with the fp32 reference) or 'bf16' (tcgen05 tensor cores, 2e-2)."""
+    global _DEFAULT_PRECISION
+    assert precision in ("fp32", "bf16")
+    _DEFAULT_PRECISION = precision
+
+
+def get_default_precision():
+    return _DEFAULT_PRECISION
+
+
+class _SparseConvFunction(torch.autograd.Function):
+    """Forward on libbevfront_b200; backward (training, SURVEY configs[2]) as gather / matmul / index_add over
+    the same rulebook.  The backward is functional plumbing in torch ops, not a tuned kernel."""
+
+    @staticmethod
+    def forward(ctx, features, weight, bias, pair_fwd, n_out, packed, precision):
+        cout, cin = weight.shape[0], weight.shape[-1]
+        kv = weight.numel() // (cout * cin)
+        out, _ = Fsp.implicit_gemm(features, pair_fwd, n_out, packed, kv, cin, cout, precision=precision, bias=bias)
+        ctx.save_for_backward(features, weight, pair_fwd)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, weight, pair_fwd = ctx.saved_tensors
+        cout, cin = weight.shape[0], weight.shape[-1]
+        kv = pair_fwd.shape[0]
+        w = weight.reshape(cout, kv, cin)
+        grad_out = grad_out.contiguous()
+        g_feat = torch.zeros_like(features) if ctx.needs_input_grad[0] else None
+        g_w = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
+        for k in range(kv):
+            idx = pair_fwd[k]
+            sel = torch.nonzero(idx >= 0, as_tuple=False).squeeze(1)
+            if sel.numel() == 0:
+                continue
+            rows = idx[sel].long()
+            go = grad_out[sel]
+            if g_feat is not None:
+                g_feat.index_add_(0, rows, go @ w[:, k, :])
+            if g_w is not None:
+                g_w[:, k, :] = go.t() @ features[rows]
+        g_b = grad_out.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return g_feat, (g_w.reshape(weight.shape) if g_w is not None else None), g_b, None, None, None, None
+
+
+class SparseConvolution(SparseModule):
+    __constants__ = ["stride", "padding", "dilation", "groups", "bias", "subm", "inverse", "transposed",
+                     "output_padding"]
+
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None, algo=None,
+                 fp32_accum=None, record_voxel_count=False, act_type=None, act_alpha=0, act_beta=0, large_kernel_fast_algo=False,
+                 name=None, precision=None):
+        super().__init__()
+        if ndim != 3:
+            raise NotImplementedError("only 3-D sparse convolutions are on the BEV front-end hot path")
+        if groups != 1:
+            raise NotImplementedError("groups != 1 is not supported")
+        if transposed or inverse:
+            raise NotImplementedError("transposed / inverse sparse convolutions are not on the BEV front-end hot path")
+        self.ndim = ndim
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = list(Fsp._triple(kernel_size))
+        self.stride = list(Fsp._triple(stride))
+        self.padding = list(Fsp._triple(padding))
+        self.dilation = list(Fsp._triple(dilation))
+        self.output_padding = list(Fsp._triple(output_padding))
+        self.conv1x1 = all(k == 1 for k in self.kernel_size)
+        self.transposed, self.inverse, self.groups, self.subm = transposed, inverse, groups, subm
+        self.indice_key = indice_key
+        self.algo = algo
+        self.fp32_accum = fp32_accum
+        self.record_voxel_count = record_voxel_count
+        self.name = name
+        self.precision = precision      # None -> module default
+        self.fuse_epilogue = True       # SparseSequential may fold eval BatchNorm1d + ReLU into this conv
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self._packed = {}
+        self.reset_parameters()
+
+    def extra_repr(self):
+        s = "{in_channels}, {out_channels}, kernel_size={kernel_size}, stride={stride}"
+        if self.padding != [0] * 3:
+            s += ", padding={padding}"
+        if self.dilation != [1] * 3:
+            s += ", dilation={dilation}"
+        if self.bias is None:
+            s += ", bias=False"
+        if self.indice_key is not None:
+            s += ", indice_key={indice_key}"
+        return s.format(**self.__dict__)
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+            bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    # ---- weights re-packed for the kernels, cached per parameter version --------------------------------
+    def _packed_weight(self, precision):
+        key = (precision, self.weight._version, self.weight.data_ptr(), self.weight.device)
+        hit = self._packed.get(precision)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        packed = Fsp.pack_weight_f32(self.weight) if precision == "fp32" else Fsp.pack_weight_bf16(self.weight)
+        self._packed[precision] = (key, packed)
+        return packed
+
+    def _resolve_precision(self):
+        p = self.precision or _DEFAULT_PRECISION
+        if p == "bf16" and not Fsp.tc_supported(self.in_channels, self.out_channels):
+            raise RuntimeError(f"bf16 tensor-core path does not support {self.in_channels}->{self.out_channels} "
+                               "channels; use precision='fp32' for this layer")
+        return p
+
+    def _rulebook(self, input):
+        ksize, stride = tuple(self.kernel_size), tuple(self.stride)
+        padding, dilation = tuple(self.padding), tuple(self.dilation)
+        key = self.indice_key
+        datas = input.find_indice_pair(key)
+        if datas is not None:
+            if self.subm:
+                assert datas.subm and datas.ksize == ksize and datas.dilation == dilation, \
+                    f"indice_key {key!r} is shared by layers with different geometry"
+            else:
+                assert not datas.subm and datas.matches(ksize, stride, padding, dilation, False), \
+                    f"indice_key {key!r} is shared by layers with different geometry"
+            return datas
+        if self.subm and key is None:
+            # the reference passes indice_key=None to every SubM conv of SparseBasicBlock
+            # (middle_encoders/sparse_encoder.py:171,222-226) so spconv rebuilds the same rulebook 16 times;
+            # equal geometry on the same sites gives the same rulebook, so cache it under a derived key
+            auto = ("__subm__", ksize, dilation)
+            datas = input.indice_dict.get(auto)
+            if datas is not None and datas.out_indices.data_ptr() == input.indices.data_ptr():
+                return datas
+            datas = Fsp.get_indice_pairs(input, ksize, stride, padding, dilation, True)
+            input.indice_dict[auto] = datas
+            return datas
+        datas = Fsp.get_indice_pairs(input, ksize, stride, padding, dilation, self.subm)
+        if key is not None:
+            input.indice_dict[key] = datas
+        return datas
+
+    def forward(self, input, bn_scale=None, bn_shift=None, residual=None, relu=False):
+        assert isinstance(input, SparseConvTensor)
+        assert input.features.shape[1] == self.in_channels, "channel size mismatch"
+        precision = self._resolve_precision()
+        datas = self._rulebook(input)
+        out = input.shadow_copy()
+        out._bf16 = None
+        if not self.subm:
+            out.indices = datas.out_indices
+            out.spatial_shape = list(datas.out_spatial_shape)
+            out._index = datas.out_index
+            out._sorted_rows = True
+        n_out = datas.n_out
+        needs_grad = torch.is_grad_enabled() and (input.features.requires_grad or self.weight.requires_grad)
+        fused = bn_scale is not None or residual is not None or relu
+        if needs_grad:
+            assert not fused, "fused BN/ReLU epilogues are inference-only"
+            feats = _SparseConvFunction.apply(input.features, self.weight, self.bias, datas.pair_fwd, n_out,
+                                              self._packed_weight(precision), precision)
+        else:
+            kv = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+            feats, fb = Fsp.implicit_gemm(input.features, datas.pair_fwd, n_out, self._packed_weight(precision), kv,
+                                          self.in_channels, self.out_channels, precision=precision,
+                                          bias=self.bias, bn_scale=bn_scale, bn_shift=bn_shift, residual=residual,
+                                          relu=relu, features_bf16=input._bf16, want_bf16=(precision == "bf16"))
+            out._bf16 = fb
+        out._features = feats
+        return out
+
+
+class SubMConv3d(SparseConvolution):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, fp32_accum=None, large_kernel_fast_algo=False, name=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key, algo=algo, fp32_accum=fp32_accum, name=name, **kwargs)
+
+
+class SparseConv3d(SparseConvolution):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, fp32_accum=None, record_voxel_count=False, large_kernel_fast_algo=False,
+                 name=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         indice_key=indice_key, algo=algo, fp32_accum=fp32_accum,
+                         record_voxel_count=record_voxel_count, name=name, **kwargs)

@@ -1,0 +1,139 @@
+"""Rulebook generation and gather-GEMM-scatter: the functional boundary spconv exposes as
+SpconvOps.get_indice_pairs_implicit_gemm / ConvGemmOps.implicit_gemm (reference call sites
+projects/SparseConvolution/sparse_functional.py:118-137, 287-314), on libbevfront_b200.
+"""
+import ctypes
+
+import torch
+
+from .._lib import check, cur_stream, i32_array, lib, ptr
+from .core import CoordIndex, IndicePair
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return tuple(int(x) for x in v)
+    return (int(v),) * 3
+
+
+def conv_out_shape(spatial_shape, ksize, stride, padding, dilation):
+    out = (ctypes.c_int * 3)()
+    lib().bevf_spconv_out_shape(i32_array(spatial_shape), i32_array(ksize), i32_array(stride), i32_array(padding),
+                                i32_array(dilation), out)
+    return [int(v) for v in out]
+
+
+def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
+    """x: SparseConvTensor -> IndicePair.  SubM: out sites == in sites (same order).  Strided: out sites in
+    ascending linear order; ONE host sync to learn n_out (spconv returns num_act_out to the host as well)."""
+    ksize, stride, padding, dilation = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    dev = x.indices.device
+    L = lib()
+    kv = ksize[0] * ksize[1] * ksize[2]
+    n_in = x.indices.shape[0]
+    in_index = x.coord_index()
+    with torch.cuda.device(dev):
+        st = cur_stream(dev)
+        if subm:
+            pair = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
+            check(L.bevf_spconv_subm_rulebook(ptr(x.indices), int(n_in), x.batch_size, in_index.shape_c,
+                                              i32_array(ksize), i32_array(dilation), ptr(in_index.mem),
+                                              ctypes.c_size_t(in_index.nbytes), ptr(in_index.perm), ptr(pair),
+                                              int(n_in), st))
+            return IndicePair(x.indices, pair, n_in, list(x.spatial_shape), in_index, in_index, ksize, (1, 1, 1),
+                              padding, dilation, True)
+        out_shape = conv_out_shape(x.spatial_shape, ksize, stride, padding, dilation)
+        reach = 1
+        for k, s in zip(ksize, stride):
+            reach *= min(k, -(-k // s))
+        cells = x.batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+        cap = max(1, min(n_in * reach, cells))
+        out_bytes = int(L.bevf_spconv_index_bytes(x.batch_size, i32_array(out_shape)))
+        if out_bytes == 0:
+            raise RuntimeError("sparse grid not supported: " + L.bevf_last_error().decode())
+        out_mem = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+        out_indices = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+        n_out_dev = torch.empty(1, dtype=torch.int32, device=dev)
+        check(L.bevf_spconv_strided_sites(ptr(x.indices), int(n_in), x.batch_size, in_index.shape_c, i32_array(ksize),
+                                          i32_array(stride), i32_array(padding), i32_array(dilation), ptr(out_mem),
+                                          ctypes.c_size_t(out_bytes), ptr(out_indices), int(cap), ptr(n_out_dev), st))
+        n_out = int(n_out_dev.item())
+        assert n_out <= cap
+        out_indices = out_indices[:n_out]
+        pair = torch.empty((kv, max(n_out, 1)), dtype=torch.int32, device=dev)
+        check(L.bevf_spconv_strided_rulebook(ptr(out_indices), int(n_out), None, x.batch_size, in_index.shape_c,
+                                             i32_array(ksize), i32_array(stride), i32_array(padding),
+                                             i32_array(dilation), ptr(in_index.mem), ctypes.c_size_t(in_index.nbytes),
+                                             ptr(in_index.perm), ptr(pair), int(max(n_out, 1)), st))
+        out_index = CoordIndex(out_indices, x.batch_size, out_shape, mem=out_mem)
+        return IndicePair(out_indices, pair[:, :n_out] if n_out else pair[:, :0], n_out, out_shape, in_index,
+                          out_index, ksize, stride, padding, dilation, False)
+
+
+def pack_weight_f32(weight):
+    """[Cout, kD, kH, kW, Cin] fp32 -> [kv, Cin, Cout] fp32."""
+    cout, cin = weight.shape[0], weight.shape[-1]
+    kv = weight.numel() // (cout * cin)
+    w = weight.detach().contiguous().float()
+    out = torch.empty((kv, cin, cout), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib().bevf_spconv_pack_weight_f32(ptr(w), ptr(out), int(kv), int(cin), int(cout), cur_stream(w.device)))
+    return out
+
+
+def pack_weight_bf16(weight):
+    """[Cout, kD, kH, kW, Cin] fp32 -> per-tap UMMA core-matrix image, bf16 [kv, Cout*cin_pad]."""
+    cout, cin = weight.shape[0], weight.shape[-1]
+    kv = weight.numel() // (cout * cin)
+    L = lib()
+    cin_pad = L.bevf_spconv_tc_cin_pad(int(cin))
+    w = weight.detach().contiguous().float()
+    out = torch.empty((kv, cout * cin_pad), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        check(L.bevf_spconv_pack_weight_bf16(ptr(w), ptr(out), int(kv), int(cin), int(cout), cur_stream(w.device)))
+    return out
+
+
+def cast_features_bf16(features, cin_pad):
+    n, cin = features.shape
+    f = features.contiguous().float()
+    out = torch.empty((n, cin_pad), dtype=torch.bfloat16, device=f.device)
+    with torch.cuda.device(f.device):
+        check(lib().bevf_spconv_cast_bf16(ptr(f), ptr(out), int(n), int(cin), int(cin_pad), None, cur_stream(f.device)))
+    return out
+
+
+def tc_supported(cin, cout):
+    return bool(lib().bevf_spconv_tc_supported(int(cin), int(cout)))
+
+
+def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, precision="fp32", bias=None, bn_scale=None,
+                  bn_shift=None, residual=None, relu=False, features_bf16=None, want_bf16=False):
+    """out[n_out, Cout] fp32 (and optionally its bf16 copy) = epilogue(sum_k feats[pair_fwd[k]] @ W[k])."""
+    dev = pair_fwd.device
+    L = lib()
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
+    out_bf16 = None
+    ld = pair_fwd.stride(0) if pair_fwd.shape[1] > 0 else max(n_out, 1)
+    if residual is not None:
+        residual = residual.contiguous().float()
+    with torch.cuda.device(dev):
+        st = cur_stream(dev)
+        if precision == "fp32":
+            f = features.contiguous().float()
+            check(L.bevf_spconv_gemm_f32(ptr(f), ptr(weight_packed), ptr(pair_fwd), int(ld), int(n_out), None, int(kv),
+                                         int(cin), int(cout), ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(residual),
+                                         int(bool(relu)), ptr(out), st))
+        elif precision == "bf16":
+            cin_pad = L.bevf_spconv_tc_cin_pad(int(cin))
+            fb = features_bf16 if features_bf16 is not None else cast_features_bf16(features, cin_pad)
+            assert fb.shape[1] == cin_pad and fb.dtype == torch.bfloat16
+            if want_bf16:
+                out_bf16 = torch.empty((n_out, cout), dtype=torch.bfloat16, device=dev)
+            check(L.bevf_spconv_gemm_bf16(ptr(fb), ptr(weight_packed), ptr(pair_fwd), int(ld), int(n_out), None,
+                                          int(kv), int(cin_pad), int(cout), ptr(bias), ptr(bn_scale), ptr(bn_shift),
+                                          ptr(residual), int(bool(relu)), ptr(out), ptr(out_bf16), st))
+        else:
+            raise ValueError(f"unknown precision {precision!r}")
+    return out, out_bf16

@@ -182,6 +182,93 @@ int bevf_bev_pool_fused_backward(const float *out_grad_nhwc, const float *depth,
 int bevf_nchw_to_nhwc(const float *src, float *dst, int n, int c, int hw, void *stream);
 int bevf_nhwc_to_nchw(const float *src, float *dst, int n, int c, int hw, void *stream);
 
+/* ------------------------------------------------------------------------------------------------ *
+ * Sparse 3-D convolution (SubMConv3d / SparseConv3d of spconv >= 2.3, the third-party dependency the
+ * reference builds its encoder from: mmdet3d/models/layers/spconv/overwrite_spconv/write_spconv2.py:21-38,
+ * mmdet3d/models/layers/sparse_block.py:201-217, projects/BEVFusion/bevfusion/sparse_encoder.py:131-147;
+ * functional boundary documented by projects/SparseConvolution/sparse_functional.py:70-162, 220-320).
+ *
+ * Conventions: indices [n,4] int32 = (batch, x, y, z), 16-byte aligned; spatial shape (X, Y, Z); kernel taps
+ * row-major over (kx, ky, kz) = the (kD,kH,kW) axes of the weight W[Cout, kD, kH, kW, Cin]; cross-correlation
+ * out[o] = sum_k W[:,k,:] . in[o*stride - pad + k*dil]; SubM: out sites == in sites (same order), kernel
+ * centred; strided conv: out sites in ASCENDING LINEAR ORDER ((b*OX + x)*OY + y)*OZ + z.
+ * pair_fwd [kv, ld] int32: input row feeding output j under tap k, or -1 (spconv's PairFwd layout).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* out = (in + 2p - d(k-1) - 1)/s + 1 per axis.  Host-only helper. */
+int bevf_spconv_out_shape(const int *shape_host, const int *ksize_host, const int *stride_host,
+                          const int *padding_host, const int *dilation_host, int *out_shape_host);
+
+/*
+ * Coordinate index of one sparse level: occupancy bitmap over (batch, X, Y, Z) + popcount prefix.
+ * bevf_spconv_index_build marks `indices`, scans, and, if perm != NULL, writes perm[rank] = row
+ * (rank = position in ascending linear order).  Pass perm for tensors whose rows are not sorted (the
+ * voxelizer output); levels produced by bevf_spconv_strided_sites are sorted and need none.
+ * bevf_spconv_index_error_flag returns a device int inside index_mem: 0 ok, 1 coordinate outside the
+ * grid, 2 duplicate coordinate.
+ */
+size_t bevf_spconv_index_bytes(int batch, const int *shape_host);
+int bevf_spconv_index_build(const int *indices, int n, int batch, const int *shape_host, void *index_mem,
+                            size_t index_bytes, int *perm, void *stream);
+const int *bevf_spconv_index_error_flag(void *index_mem, size_t index_bytes, int batch, const int *shape_host);
+
+/* SubM rulebook: pair_fwd[k, j] = row of the input at indices[j] + (k - ksize/2) * dilation, or -1. */
+int bevf_spconv_subm_rulebook(const int *indices, int n, int batch, const int *shape_host, const int *ksize_host,
+                              const int *dilation_host, const void *index_mem, size_t index_bytes,
+                              const int *perm, int *pair_fwd, int ld, void *stream);
+
+/*
+ * Strided (regular) sparse conv, step 1: output sites.  Builds the OUTPUT level's coordinate index in
+ * out_index_mem (sized with bevf_spconv_index_bytes(batch, out_shape)), writes out_indices[min(n_out,cap),4]
+ * in ascending linear order and n_out to *n_out_dev.  cap = rows available in out_indices
+ * (n_in * min(kv, prod(ceil(k/s))) always suffices).
+ */
+int bevf_spconv_strided_sites(const int *in_indices, int n_in, int batch, const int *in_shape_host,
+                              const int *ksize_host, const int *stride_host, const int *padding_host,
+                              const int *dilation_host, void *out_index_mem, size_t out_index_bytes,
+                              int *out_indices, int cap, int *n_out_dev, void *stream);
+/* step 2: pair_fwd[k, j] = row of the input at out[j]*stride - pad + k*dil, or -1.  n_out may be given on the
+ * host, or (n_out_dev != NULL) read from the device with rows >= *n_out_dev left untouched. */
+int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, const int *n_out_dev, int batch,
+                                 const int *in_shape_host, const int *ksize_host, const int *stride_host,
+                                 const int *padding_host, const int *dilation_host, const void *in_index_mem,
+                                 size_t in_index_bytes, const int *in_perm, int *pair_fwd, int ld, void *stream);
+
+/* SparseConvTensor.dense(): dense[B, C, X, Y, Z] (bev_layout == 0) or the BEVFusionSparseEncoder tail
+ * (sparse_encoder.py:147-151) dense().permute(0,1,4,2,3).view(B, C*Z, X, Y) (bev_layout != 0).  Fully written. */
+int bevf_sparse_to_dense(const float *feats, const int *indices, int n, int c, int batch, const int *shape_host,
+                         float *dense, int bev_layout, void *stream);
+
+/*
+ * Gather-GEMM-scatter (replaces ConvGemmOps.implicit_gemm).  out[j, :] = epilogue(sum_k feats[pair_fwd[k,j], :]
+ * @ W[k]) with the optional fused epilogue v = acc + bias; v = v*bn_scale + bn_shift; v += residual[j];
+ * v = max(v, 0)  (what mmdet3d/models/layers/sparse_block.py:137-154 applies after every conv in eval mode).
+ * n_out rows are computed; with n_out_dev != NULL the row count is read from the device (<= ld).
+ *
+ * fp32 (parity path, FFMA): weights repacked once to [kv, Cin, Cout] with bevf_spconv_pack_weight_f32 from the
+ * spconv-2.x parameter layout [Cout, kD, kH, kW, Cin].
+ */
+int bevf_spconv_pack_weight_f32(const float *weight_okc, float *weight_kio, int kv, int cin, int cout, void *stream);
+int bevf_spconv_gemm_f32(const float *feats, const float *weight_kio, const int *pair_fwd, int ld, int n_out,
+                         const int *n_out_dev, int kv, int cin, int cout, const float *bias, const float *bn_scale,
+                         const float *bn_shift, const float *residual, int relu, float *out, void *stream);
+/*
+ * bf16 tensor-core path (tcgen05.mma, fp32 accumulation in TMEM): features bf16 [n, cin_pad] (cin_pad =
+ * bevf_spconv_tc_cin_pad(cin) in {16,32,64,128}, zero padded: bevf_spconv_cast_bf16), weights packed per tap into
+ * the UMMA K-major core-matrix image (bevf_spconv_pack_weight_bf16, kv*cout*cin_pad bf16).  Cout in
+ * {16,32,64,128}.  Writes fp32 (out_f32) and/or bf16 (out_bf16, feeds the next layer without a cast pass).
+ */
+int bevf_spconv_tc_cin_pad(int cin);
+int bevf_spconv_tc_supported(int cin, int cout);
+int bevf_spconv_cast_bf16(const float *src, void *dst_bf16, int n, int cin, int cin_pad, const int *n_dev,
+                          void *stream);
+int bevf_spconv_pack_weight_bf16(const float *weight_okc, void *weight_packed, int kv, int cin, int cout,
+                                 void *stream);
+int bevf_spconv_gemm_bf16(const void *feats_bf16, const void *weight_packed, const int *pair_fwd, int ld, int n_out,
+                          const int *n_out_dev, int kv, int cin_pad, int cout, const float *bias,
+                          const float *bn_scale, const float *bn_shift, const float *residual, int relu,
+                          float *out_f32, void *out_bf16, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
