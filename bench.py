@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""BEV front-end throughput on B200 (BASELINE.json metric: frames/s; bev_pool / voxelize GB/s and sparse-conv TFLOP/s
+against the measured peaks).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision bf16|fp32]
+
+One "step" = one synthetic nuScenes-shaped frame through the front end on each GPU (weak scaling: frames are
+independent, no data-path collective): 10-sweep LiDAR voxelize(+mean) -> 21-conv sparse encoder -> dense BEV, and
+6-camera (depth, context) -> fused bev_pool -> BEV.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+# the CPU arm mixes two OpenMP runtimes (torch's and the C oracle's); spinning idle threads of one steal the cores of
+# the other (3x slower), so both are told to sleep when idle.  Must be set before either runtime loads.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
+RING = 8                       # distinct frames the timed loop rotates over (8 x 20 MB inputs > 126 MB L2)
+N_CAMS, D_BINS, C_CTX, FEAT = 6, 118, 80, (32, 88)
+METRIC = "bev_frontend_frames_per_sec"
+WORKLOAD = ("configs[1]: BEVFusion camera+LiDAR nuScenes front end, batch 1, 10-sweep ~320k pts x 5 dims, "
+            "1440x1440x41 sparse grid (hard voxelize max 10 pts / 160000 voxels + mean, 21-conv sparse encoder), "
+            "6 cams x 118 depth x 32x88 x 80 ch fused bev_pool -> 360x360")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tc=float(d["bf16_tflops"]), tc_sustained=float(d["bf16_tflops_sustained"]),
+                    src="measured")
+    return dict(hbm=6650.0, tc=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+def make_frames(n, seed0=0):
+    from bevfusion_3d_object_detection_b200 import synthetic
+
+    frames = []
+    for i in range(n):
+        pts = synthetic.lidar_sweeps(seed=seed0 + i)
+        depth, ctx = synthetic.camera_features(N_CAMS, D_BINS, C_CTX, FEAT, batch=1, seed=seed0 + i)
+        frames.append(dict(points=pts, depth=depth, ctx=ctx))
+    return frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU formulation on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+class CpuFrontEnd:
+    def __init__(self, seed=0):
+        import torch
+
+        import oracle
+        from oracle import cpu_frontend
+        from bevfusion_3d_object_detection_b200 import frontend, synthetic
+
+        oracle.build()
+        self.t, self.cf, self.syn = torch, cpu_frontend, synthetic
+        torch.manual_seed(seed)
+        enc = frontend.BEVFusionSparseEncoder(**frontend.NUSCENES_ENCODER_CFG).eval()
+        self.plan = cpu_frontend.encoder_plan(enc)
+        self.vcfg = frontend.NUSCENES_VOXELIZE_CFG
+        vt = frontend.BaseViewTransform(**frontend.NUSCENES_VIEW_CFG)
+        rig = {k: torch.from_numpy(v) for k, v in synthetic.camera_rig(N_CAMS, (256, 704), 1).items()}
+        with torch.no_grad():
+            geom = vt.get_geometry(**rig)
+            self.geom_feats, self.kept, _, self.indices = vt.bev_pool_aux(geom)
+        self.nx = [int(v) for v in vt.nx]
+        self.cores = torch.get_num_threads()
+        self.kind = "reference" if cpu_frontend.ref_voxel_module() is not None else "port"
+
+    def step(self, frame):
+        t, cf = self.t, self.cf
+        with t.no_grad():
+            feats, coords, _ = cf.cpu_voxelize_mean(frame["points"], self.vcfg["voxel_size"],
+                                                    self.vcfg["point_cloud_range"], self.vcfg["max_num_points"],
+                                                    self.vcfg["max_voxels"][1])
+            lidar = cf.cpu_sparse_encoder(self.plan, feats, coords.numpy(), [1440, 1440, 41], 1)
+            cam = cf.cpu_bev_pool(t.from_numpy(frame["depth"]), t.from_numpy(frame["ctx"]), self.kept, self.indices,
+                                  self.geom_feats, 1, N_CAMS, self.nx[2], self.nx[0], self.nx[1])
+        return lidar, cam
+
+    def describe(self):
+        v = "reference C++ hard_voxelize_cpu (oracle/_ref)" if self.kind == "reference" else "C port of hard_voxelize"
+        return (f"one full frame per step: {v} + torch gather-mm-scatter sparse encoder (mmcv CPU indice_conv "
+                f"formulation, rulebook from the C oracle) + torch outer-product/index_add_ bev_pool")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cpu = CpuFrontEnd()
+    frames = make_frames(2)
+    for i in range(args.warmup):
+        cpu.step(frames[i % len(frames)])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu.step(frames[i % len(frames)])
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference", config=dict(workload=WORKLOAD),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=cpu.cores, kind=cpu.kind, sample=cpu.describe()),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from bevfusion_3d_object_detection_b200 import _lib, frontend, spconv, synthetic
+    from bevfusion_3d_object_detection_b200.spconv import functional as Fsp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    pk = peaks()
+
+    torch.manual_seed(0)
+    model = frontend.BEVFrontEnd(precision=args.precision).to(dev).eval()
+    rig = {k: torch.from_numpy(v).to(dev) for k, v in synthetic.camera_rig(N_CAMS, (256, 704), 1).items()}
+    tables = model.set_calibration(rig)
+
+    frames = make_frames(RING, seed0=100 * rank)
+    dev_frames = [{k: torch.from_numpy(v).to(dev) for k, v in f.items()} for f in frames]
+    pin_frames = [{k: torch.from_numpy(v).pin_memory() for k, v in f.items()} for f in frames]
+
+    def step_dev(i):
+        f = dev_frames[i % RING]
+        return model([f["points"]], f["depth"], f["ctx"], tables)
+
+    out_host = {}
+
+    def step_e2e(i):
+        f = pin_frames[i % RING]
+        pts = f["points"].to(dev, non_blocking=True)
+        depth = f["depth"].to(dev, non_blocking=True)
+        ctx = f["ctx"].to(dev, non_blocking=True)
+        lidar, cam = model([pts], depth, ctx, tables)
+        if not out_host:
+            out_host["lidar"] = torch.empty(lidar.shape, dtype=lidar.dtype).pin_memory()
+            out_host["cam"] = torch.empty(cam.shape, dtype=cam.dtype).pin_memory()
+        out_host["lidar"].copy_(lidar, non_blocking=True)
+        out_host["cam"].copy_(cam, non_blocking=True)
+        return lidar, cam
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = L.bevf_launch_count()
+            e0.record()
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            launches = L.bevf_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+
+    # ---- per-stage device times (same rotating inputs), for the roofline objects -------------------------------
+    def stage_ms(fn, steps):
+        with torch.no_grad():
+            for i in range(3):
+                fn(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                fn(3 + i)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ss = max(5, min(args.steps, 20))
+    vox_out = {}
+
+    def f_vox(i):
+        vox_out["v"] = model.voxelize([dev_frames[i % RING]["points"]])
+
+    ms_vox = stage_ms(f_vox, ss)
+    feats, coords, _ = vox_out["v"]
+    n_pts = int(dev_frames[(3 + ss - 1) % RING]["points"].shape[0])
+    m_vox = int(feats.shape[0])
+
+    def f_pool(i):
+        f = dev_frames[i % RING]
+        model.extract_img_bev(f["depth"], f["ctx"], tables)
+
+    ms_pool = stage_ms(f_pool, ss)
+
+    Fsp.GEMM_TIMING = []
+    with torch.no_grad():
+        model.pts_middle_encoder(feats, coords, 1)
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in Fsp.GEMM_TIMING)
+    gemm_flops = sum(fl for _, _, fl in Fsp.GEMM_TIMING)
+    n_gemm = len(Fsp.GEMM_TIMING)
+    Fsp.GEMM_TIMING = None
+
+    def f_enc(i):
+        model.pts_middle_encoder(feats, coords, 1)
+
+    ms_enc = stage_ms(f_enc, ss)
+
+    c_pts = 5
+    vox_bytes = 4 * c_pts * n_pts + m_vox * (4 * c_pts + 16 + 4)
+    fh, fw = FEAT
+    pool_bytes = (4 * N_CAMS * fh * fw * (D_BINS + C_CTX) + 4 * tables.nk + 8 * tables.n_intervals
+                  + 4 * C_CTX * 360 * 360)
+    stages = dict(
+        voxelize_mean=dict(ms=ms_vox, bytes=vox_bytes, gbs=vox_bytes / ms_vox / 1e6, frac=vox_bytes / ms_vox / 1e6 / pk["hbm"],
+                           points=n_pts, voxels=m_vox),
+        bev_pool_fused=dict(ms=ms_pool, bytes=pool_bytes, gbs=pool_bytes / ms_pool / 1e6,
+                            frac=pool_bytes / ms_pool / 1e6 / pk["hbm"], nk=tables.nk, n_intervals=tables.n_intervals),
+        sparse_encoder=dict(ms=ms_enc, gemm_ms=gemm_ms, gemm_launches=n_gemm, gemm_flops=gemm_flops,
+                            gemm_tflops=gemm_flops / max(gemm_ms, 1e-9) / 1e9,
+                            gemm_frac=gemm_flops / max(gemm_ms, 1e-9) / 1e9 / pk["tc"]))
+    # the dominant kernel family of the step
+    if gemm_ms >= max(ms_vox, ms_pool):
+        roof = dict(kernel="spconv_tc_kernel (21 launches, aggregate)", bound="tensor",
+                    achieved=stages["sparse_encoder"]["gemm_tflops"], peak=pk["tc"], unit="TFLOP/s",
+                    frac=stages["sparse_encoder"]["gemm_frac"], traffic=None)
+    elif ms_pool >= ms_vox:
+        roof = dict(kernel="bev_pool_fused_fwd_kernel", bound="hbm", achieved=stages["bev_pool_fused"]["gbs"],
+                    peak=pk["hbm"], unit="GB/s", frac=stages["bev_pool_fused"]["frac"], traffic=None)
+    else:
+        roof = dict(kernel="voxelize_mean (5 kernels)", bound="hbm", achieved=stages["voxelize_mean"]["gbs"],
+                    peak=pk["hbm"], unit="GB/s", frac=stages["voxelize_mean"]["frac"], traffic=None)
+    roof["peak_source"] = pk["src"]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- cpu_baseline (rank 0, N == 1 only): bounded sample = 1 warm-up + 2 timed frames ----------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = CpuFrontEnd()
+        cpu.step(frames[0])
+        t0 = time.perf_counter()
+        for i in range(2):
+            cpu.step(frames[1 + i])
+        dt = (time.perf_counter() - t0) / 2
+        cpu_baseline = dict(value=1.0 / dt, unit="frames/s", cores=cpu.cores, kind=cpu.kind,
+                            sample="2 frames after 1 warm-up; " + cpu.describe())
+
+    h2d = sum(int(v.numel() * v.element_size()) for v in pin_frames[0].values())
+    d2h = sum(int(v.numel() * v.element_size()) for v in out_host.values())
+    fps = world * args.steps / (ms / 1e3)
+    fps_e2e = world * args.steps / (ms_e2e / 1e3)
+    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=("bf16 sparse conv (fp32 accumulate) + fp32 voxelize/bev_pool" if args.precision == "bf16"
+                       else "f32"),
+                data="synthetic",
+                config=dict(workload=WORKLOAD, frames_per_gpu_per_step=1, precision=args.precision,
+                            l2="inputs rotate over %d distinct frames (%.0f MB > 126 MB L2)" % (RING, RING * h2d / 1e6),
+                            parallelism="frame-parallel, no data-path collective"),
+                e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches), roofline=roof, stages=stages, cpu_baseline=cpu_baseline, clocks=clocks)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BEVFRONT_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ def _declare(lib):
         if hasattr(lib, name):
             getattr(lib, name).restype = c_size_t
     lib.bevf_spconv_index_error_flag.restype = c_void_p
+    lib.bevf_launch_count.restype = ctypes.c_longlong
     _ = c_int
     return lib
 

@@ -12,6 +12,8 @@ namespace bevf {
 
 // thread-local last-error text (bevf_last_error)
 void set_error(const char *fmt, ...);
+// process-wide count of kernel launches issued by this library (bevf_launch_count)
+void count_launch();
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -53,4 +55,8 @@ constexpr int kNumSMs = 148;  // B200
     }                                                                                          \
   } while (0)
 
-#define BEVF_CHECK_LAUNCH() BEVF_CHECK_CUDA(cudaGetLastError())
+#define BEVF_CHECK_LAUNCH()             \
+  do {                                  \
+    bevf::count_launch();               \
+    BEVF_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)

@@ -1,0 +1,62 @@
+"""The BEV feature-construction front end as one object: LiDAR points -> voxelize -> sparse encoder -> BEV map,
+and camera (depth, context) -> fused bev_pool -> BEV map.  It wires the three operators exactly where the
+reference's detector does:
+
+  BEVFusion.voxelize            projects/BEVFusion/bevfusion/bevfusion.py:227-255   (hard voxelize + mean + batch pad)
+  BEVFusion.extract_pts_feat    projects/BEVFusion/bevfusion/bevfusion.py:196-225   (-> pts_middle_encoder)
+  DepthLSSTransform.forward     projects/BEVFusion/bevfusion/depth_lss.py:699-725, 179-204 (outer product + bev_pool)
+
+The dense image backbone / depthnet / fuser / head are outside the hot path: the camera branch starts
+from the depthnet's softmax depth and context feature maps.
+"""
+import torch
+from torch import nn
+
+from . import synthetic
+from .ops import Voxelization
+from .sparse_encoder import NUSCENES_ENCODER_CFG, BEVFusionSparseEncoder
+from .view_transform import BaseViewTransform
+
+NUSCENES_VOXELIZE_CFG = dict(  # configs/nuscenes/bevfusion_lidar_voxel0075_second_secfpn_8xb4-cyclic-20e_nus-3d.py:49-54
+    max_num_points=10, point_cloud_range=synthetic.NUSCENES_RANGE, voxel_size=synthetic.NUSCENES_VOXEL,
+    max_voxels=(120000, 160000))
+NUSCENES_VIEW_CFG = dict(  # configs/nuscenes/bevfusion_lidar-cam_...py:45-55
+    in_channels=256, out_channels=80, image_size=(256, 704), feature_size=(32, 88), xbound=[-54.0, 54.0, 0.3],
+    ybound=[-54.0, 54.0, 0.3], zbound=[-10.0, 10.0, 20.0], dbound=[1.0, 60.0, 0.5])
+
+
+class BEVFrontEnd(nn.Module):
+
+    def __init__(self, voxelize_cfg=None, encoder_cfg=None, view_cfg=None, precision="fp32"):
+        super().__init__()
+        self.pts_voxel_layer = Voxelization(**(voxelize_cfg or NUSCENES_VOXELIZE_CFG))
+        self.pts_middle_encoder = BEVFusionSparseEncoder(**(encoder_cfg or NUSCENES_ENCODER_CFG))
+        self.view_transform = BaseViewTransform(**(view_cfg or NUSCENES_VIEW_CFG))
+        self.precision = precision
+        for m in self.pts_middle_encoder.modules():
+            if hasattr(m, "precision") and hasattr(m, "indice_key"):
+                m.precision = precision
+
+    @torch.no_grad()
+    def set_calibration(self, rig):
+        """rig: dict of [B, N, ...] tensors (camera2lidar_rots / _trans, intrins_inverse, post_rots_inverse,
+        post_trans) -> builds the per-calibration pooling tables (deploy/voxel_detection.py:98-106 does this once
+        per rig as well)."""
+        geom = self.view_transform.get_geometry(**rig)
+        return self.view_transform.build_tables(geom)
+
+    @torch.no_grad()
+    def voxelize(self, points):
+        """bevfusion.py:227-255 with voxelize_reduce=True: list of [N_k, C] -> feats[M,C], coords[M,4], sizes[M]."""
+        return self.pts_voxel_layer.forward_mean(points)
+
+    def extract_pts_feat(self, points):
+        feats, coords, _ = self.voxelize(points)
+        return self.pts_middle_encoder(feats, coords, len(points))
+
+    def extract_img_bev(self, depth, ctx, tables=None):
+        return self.view_transform.pool_fused(depth, ctx, tables)
+
+    def forward(self, points, depth, ctx, tables=None):
+        """-> (lidar_bev [B, 256, 180, 180], camera_bev [B, 80, 360, 360])"""
+        return self.extract_pts_feat(points), self.extract_img_bev(depth, ctx, tables)

@@ -10,6 +10,11 @@ from .._lib import check, cur_stream, i32_array, lib, ptr
 from .core import CoordIndex, IndicePair
 
 
+# bench.py sets this to a list to collect (start_event, end_event, useful_flops) per GEMM launch; the flop count
+# costs a reduction + host sync per layer, so it is None on the product path
+GEMM_TIMING = None
+
+
 def _triple(v):
     if isinstance(v, (list, tuple)):
         assert len(v) == 3
@@ -118,8 +123,14 @@ def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, preci
     ld = pair_fwd.stride(0) if pair_fwd.shape[1] > 0 else max(n_out, 1)
     if residual is not None:
         residual = residual.contiguous().float()
+    timing = GEMM_TIMING
+    if timing is not None:
+        pairs = int((pair_fwd[:, :n_out] >= 0).sum().item())
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), 2.0 * pairs * cin * cout)
     with torch.cuda.device(dev):
         st = cur_stream(dev)
+        if timing is not None:
+            ev[0].record()
         if precision == "fp32":
             f = features.contiguous().float()
             check(L.bevf_spconv_gemm_f32(ptr(f), ptr(weight_packed), ptr(pair_fwd), int(ld), int(n_out), None, int(kv),
@@ -136,4 +147,7 @@ def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, preci
                                           ptr(residual), int(bool(relu)), ptr(out), ptr(out_bf16), st))
         else:
             raise ValueError(f"unknown precision {precision!r}")
+        if timing is not None:
+            ev[1].record()
+            timing.append(ev)
     return out, out_bf16

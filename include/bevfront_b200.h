@@ -37,6 +37,8 @@ int bevf_abi_version(void);
 const char *bevf_last_error(void);
 /* compute capability of the device the library was compiled for: 100 (sm_100a). */
 int bevf_compiled_arch(void);
+/* number of CUDA kernels this library has launched in this process so far (bench.py's gpu_launches). */
+long long bevf_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------ *
  * Voxelization

@@ -9,7 +9,7 @@ Two modules are produced:
                    {gz,gy,gx} but indexes [x][y][z] (voxelization_cpu.cpp:129-130 vs :75,83), so it is only
                    memory-safe on cubic grids; tests use it on cubic grids only.
   ref_voxel_fixed  the same sources with that ONE allocation changed to {gx,gy,gz} (applied with a text
-                   substitution into oracle/_ref/src_fixed/, a derived, git-ignored file) so the reference
+                   substitution into a temporary directory outside the repo, so no reference source ever lands in the tree) so the reference
                    algorithm can run on the 1440x1440x41 nuScenes grid; this is the timed CPU voxelize arm.
 """
 import os
@@ -43,8 +43,9 @@ def build(verbose=False):
         load(name="ref_voxel_asis", sources=[os.path.join(REF_SRC, f) for f in files],
              extra_cflags=["-O2"], build_directory=bd, verbose=verbose)
     if not built("ref_voxel_fixed"):
-        sd = os.path.join(OUT, "src_fixed")
-        os.makedirs(sd, exist_ok=True)
+        import tempfile
+
+        sd = tempfile.mkdtemp(prefix="bevfront_ref_src_")
         with open(os.path.join(REF_SRC, "voxelization_cpu.cpp")) as f:
             text = f.read()
         assert _ASIS in text, "reference source changed; update the substitution"

@@ -1,0 +1,343 @@
+"""Sparse convolution through the C ABI against the CPU oracle: rulebook indices bit-exact, features within 1e-5
+(fp32 path) / 2e-2 (bf16 tcgen05 path) as BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from bevfusion_3d_object_detection_b200 import spconv, synthetic
+from bevfusion_3d_object_detection_b200.sparse_encoder import (NUSCENES_ENCODER_CFG, BEVFusionSparseEncoder,
+                                                               SparseBasicBlock)
+from bevfusion_3d_object_detection_b200.spconv import functional as Fsp
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-5
+RTOL_BF16 = 2e-2
+
+
+def random_sites(rng, n, batch, shape, sort=False):
+    """n distinct (b, x, y, z) rows, clustered so that 3x3x3 neighbourhoods are populated."""
+    cells = batch * shape[0] * shape[1] * shape[2]
+    n = min(n, cells)
+    lin = rng.choice(cells, size=n, replace=False)
+    if sort:
+        lin = np.sort(lin)
+    z = lin % shape[2]
+    y = (lin // shape[2]) % shape[1]
+    x = (lin // (shape[2] * shape[1])) % shape[0]
+    b = lin // (shape[2] * shape[1] * shape[0])
+    return np.stack([b, x, y, z], 1).astype(np.int32)
+
+
+def tensor_from(idx, feats, shape, batch):
+    return spconv.SparseConvTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(idx).cuda(), shape, batch)
+
+
+RULEBOOK_CASES = [
+    # subm, ksize, stride, padding, dilation, shape, batch, n
+    (True, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), (24, 20, 9), 2, 3000),
+    (True, (3, 3, 3), (1, 1, 1), (0, 0, 0), (1, 1, 1), (64, 64, 11), 1, 20000),   # SubM ignores padding
+    (True, (1, 1, 3), (1, 1, 1), (0, 0, 0), (1, 1, 1), (16, 16, 8), 1, 500),
+    (True, (3, 3, 3), (1, 1, 1), (1, 1, 1), (2, 2, 1), (24, 20, 9), 1, 2500),
+    (False, (3, 3, 3), (2, 2, 2), (1, 1, 1), (1, 1, 1), (24, 20, 9), 2, 3000),    # spconv1/2
+    (False, (3, 3, 3), (2, 2, 2), (1, 1, 0), (1, 1, 1), (40, 40, 11), 1, 9000),   # spconv3: pad (1,1,0)
+    (False, (1, 1, 3), (1, 1, 2), (0, 0, 0), (1, 1, 1), (30, 30, 5), 2, 2000),    # conv_out
+    (False, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), (12, 12, 6), 1, 200),     # stride-1 regular conv
+    (False, (2, 2, 2), (2, 2, 2), (0, 0, 0), (1, 1, 1), (16, 16, 8), 1, 700),
+    (False, (3, 3, 3), (2, 2, 2), (1, 1, 1), (1, 1, 1), (8, 8, 4), 1, 1),          # single site
+]
+
+
+@pytest.mark.parametrize("subm,ksize,stride,padding,dilation,shape,batch,n", RULEBOOK_CASES)
+def test_rulebook_bit_exact(oracle_mod, subm, ksize, stride, padding, dilation, shape, batch, n):
+    rng = np.random.default_rng(n + shape[0])
+    idx = random_sites(rng, n, batch, shape)
+    o_idx, o_pair, o_shape = oracle_mod.spconv_rulebook(idx, shape, ksize, stride, padding, dilation, subm)
+    x = tensor_from(idx, np.zeros((idx.shape[0], 4), np.float32), list(shape), batch)
+    datas = Fsp.get_indice_pairs(x, ksize, stride, padding, dilation, subm)
+    assert x.coord_index().error_code() == 0
+    assert datas.n_out == o_idx.shape[0]
+    assert list(datas.out_spatial_shape) == [int(v) for v in o_shape]
+    np.testing.assert_array_equal(datas.out_indices.cpu().numpy()[:datas.n_out], o_idx)
+    np.testing.assert_array_equal(datas.pair_fwd.cpu().numpy(), o_pair)
+
+
+def test_rulebook_full_size_properties():
+    """Config A grid (1440 x 1440 x 41) with the voxelizer's own output (first-appearance order): every site
+    finds itself under the centre tap, the rulebook is symmetric (j in nbr_k(i) <=> i in nbr_{26-k}(j)), and the
+    strided level is sorted and duplicate-free."""
+    from bevfusion_3d_object_detection_b200 import ops
+
+    pts = torch.from_numpy(synthetic.lidar_sweeps(n_sweeps=3, seed=2)).cuda()
+    _, coors, _ = ops.voxelization(pts, synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, 10, 160000, True)
+    m = coors.shape[0]
+    idx = torch.cat([torch.zeros((m, 1), dtype=torch.int32, device="cuda"), coors], 1).contiguous()
+    x = spconv.SparseConvTensor(torch.zeros((m, 4), device="cuda"), idx, [1440, 1440, 41], 1)
+    d = Fsp.get_indice_pairs(x, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True)
+    assert x.coord_index().error_code() == 0
+    pair = d.pair_fwd
+    ar = torch.arange(m, device="cuda", dtype=torch.int32)
+    assert torch.equal(pair[13], ar)
+    for k in (0, 5, 12):
+        valid = pair[k] >= 0
+        src = pair[k][valid].long()
+        assert torch.equal(pair[26 - k][src], ar[valid])
+    s = Fsp.get_indice_pairs(x, (3, 3, 3), (2, 2, 2), (1, 1, 1), (1, 1, 1), False)
+    assert s.out_spatial_shape == [720, 720, 21]
+    oi = s.out_indices.long()
+    lin = ((oi[:, 0] * 720 + oi[:, 1]) * 720 + oi[:, 2]) * 21 + oi[:, 3]
+    assert bool((lin[1:] > lin[:-1]).all())
+    # every input feeds exactly its reachable outputs: total pairs = sum over inputs of taps that divide
+    assert int((s.pair_fwd >= 0).sum()) >= m
+    # each input row appears at least once
+    seen = torch.zeros(m, dtype=torch.bool, device="cuda")
+    seen[s.pair_fwd[s.pair_fwd >= 0].long()] = True
+    assert bool(seen.all())
+
+
+def test_index_flags_bad_coordinates():
+    idx = np.array([[0, 1, 1, 1], [0, 1, 1, 1], [0, 2, 2, 2]], np.int32)
+    x = tensor_from(idx, np.zeros((3, 4), np.float32), [4, 4, 4], 1)
+    assert x.coord_index().error_code() == 2
+    idx = np.array([[0, 1, 1, 1], [0, 4, 1, 1]], np.int32)
+    x = tensor_from(idx, np.zeros((2, 4), np.float32), [4, 4, 4], 1)
+    assert x.coord_index().error_code() == 1
+
+
+def _conv_case(rng, cin, cout, ksize, n, shape, batch, subm, stride, padding, bias):
+    idx = random_sites(rng, n, batch, shape)
+    feats = rng.standard_normal((idx.shape[0], cin)).astype(np.float32)
+    kv = int(np.prod(ksize))
+    w = (rng.standard_normal((cout, *ksize, cin)) / np.sqrt(kv * cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32) if bias else None
+    cls = spconv.SubMConv3d if subm else spconv.SparseConv3d
+    conv = cls(cin, cout, ksize, stride=stride, padding=padding, bias=bias).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w))
+        if bias:
+            conv.bias.copy_(torch.from_numpy(b))
+    return idx, feats, w, b, conv
+
+
+def _oracle_conv(oracle_mod, idx, feats, w, b, shape, ksize, stride, padding, subm):
+    o_idx, o_pair, o_shape = oracle_mod.spconv_rulebook(idx, shape, ksize, stride, padding, 1, subm)
+    ref = oracle_mod.spconv_gemm(feats, w, o_pair, bias=b)
+    l1 = oracle_mod.spconv_gemm(np.abs(feats), np.abs(w), o_pair, bias=None if b is None else np.abs(b))
+    return o_idx, ref, l1
+
+
+GEMM_CASES = [
+    # cin, cout, ksize, subm, stride, padding, bias, n
+    (5, 16, (3, 3, 3), True, 1, 1, False, 4000),      # conv_input (nuScenes)
+    (3, 16, (3, 3, 3), True, 1, 1, False, 1500),      # conv_input (custom 3-dim points)
+    (16, 16, (3, 3, 3), True, 1, 1, True, 4000),
+    (16, 32, (3, 3, 3), False, 2, 1, False, 4000),
+    (32, 32, (3, 3, 3), True, 1, 1, False, 3000),
+    (32, 64, (3, 3, 3), False, 2, 1, False, 3000),
+    (64, 64, (3, 3, 3), True, 1, 1, False, 2500),
+    (64, 128, (3, 3, 3), False, 2, (1, 1, 0), False, 2500),
+    (128, 128, (3, 3, 3), True, 1, 1, False, 2000),
+    (128, 128, (1, 1, 3), False, (1, 1, 2), 0, False, 2000),
+    (7, 10, (3, 3, 3), True, 1, 1, True, 300),        # odd channel counts -> scalar paths
+]
+
+
+@pytest.mark.parametrize("cin,cout,ksize,subm,stride,padding,bias,n", GEMM_CASES)
+def test_conv_fp32_matches_oracle(oracle_mod, cin, cout, ksize, subm, stride, padding, bias, n):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    shape, batch = [20, 18, 9], 2
+    idx, feats, w, b, conv = _conv_case(rng, cin, cout, ksize, n, shape, batch, subm, stride, padding, bias)
+    conv.precision = "fp32"
+    o_idx, ref, l1 = _oracle_conv(oracle_mod, idx, feats, w, b, shape, ksize, stride, padding, subm)
+    with torch.no_grad():
+        out = conv(tensor_from(idx, feats, shape, batch))
+    np.testing.assert_array_equal(out.indices.cpu().numpy(), o_idx)
+    got = out.features.cpu().numpy()
+    assert got.shape == ref.shape
+    err = np.abs(got - ref)
+    # fp32 accumulation in a different order than the fp64 checker: 1e-5 relative + 1e-6 of sum |a||w|
+    assert (err <= RTOL_F32 * np.abs(ref) + 1e-6 * l1).all(), float(err.max())
+
+
+@pytest.mark.parametrize("cin,cout,ksize,subm,stride,padding,bias,n", GEMM_CASES[:-1])
+def test_conv_bf16_tensor_core_matches_oracle(oracle_mod, cin, cout, ksize, subm, stride, padding, bias, n):
+    rng = np.random.default_rng(cin * 1000 + cout + 7)
+    shape, batch = [20, 18, 9], 2
+    idx, feats, w, b, conv = _conv_case(rng, cin, cout, ksize, n, shape, batch, subm, stride, padding, bias)
+    conv.precision = "bf16"
+    # the checker sees the same bf16-rounded operands; what is left is fp32 accumulation order in TMEM
+    fq = torch.from_numpy(feats).bfloat16().float().numpy()
+    wq = torch.from_numpy(w).bfloat16().float().numpy()
+    o_idx, ref_q, l1 = _oracle_conv(oracle_mod, idx, fq, wq, b, shape, ksize, stride, padding, subm)
+    _, ref, _ = _oracle_conv(oracle_mod, idx, feats, w, b, shape, ksize, stride, padding, subm)
+    with torch.no_grad():
+        out = conv(tensor_from(idx, feats, shape, batch))
+    np.testing.assert_array_equal(out.indices.cpu().numpy(), o_idx)
+    got = out.features.cpu().numpy()
+    err_q = np.abs(got - ref_q)
+    assert (err_q <= 1e-5 * np.abs(ref_q) + 2e-6 * l1).all(), float(err_q.max())
+    # against the un-rounded fp32 reference: north_star's bf16 tolerance, relative to the output scale
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= RTOL_BF16 * scale
+    assert out._bf16 is not None
+    np.testing.assert_allclose(out._bf16.float().cpu().numpy(), got, rtol=1e-2, atol=1e-2 * scale)
+
+
+def test_fused_epilogue_matches_unfused(oracle_mod):
+    """SparseBasicBlock in eval mode (BN + residual + ReLU folded into the GEMM epilogue) == the oracle chain
+    conv -> bn -> relu -> conv -> bn -> +identity -> relu (sparse_block.py:137-154)."""
+    rng = np.random.default_rng(11)
+    shape, batch, c = [20, 18, 9], 2, 32
+    idx = random_sites(rng, 3000, batch, shape)
+    feats = rng.standard_normal((idx.shape[0], c)).astype(np.float32)
+    blk = SparseBasicBlock(c, c, norm_cfg=dict(type="BN1d", eps=1e-3, momentum=0.01)).cuda().eval()
+    for bn in (blk.bn1, blk.bn2):
+        with torch.no_grad():
+            bn.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, c).astype(np.float32)))
+            bn.bias.copy_(torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.1))
+            bn.running_mean.copy_(torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.1))
+            bn.running_var.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, c).astype(np.float32)))
+    with torch.no_grad():
+        out = blk(tensor_from(idx, feats, shape, batch)).features.cpu().numpy()
+    _, pair, _ = oracle_mod.spconv_rulebook(idx, shape, (3, 3, 3), 1, 1, 1, True)
+
+    def bn_args(bn):
+        return [t.detach().cpu().numpy() for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)] + [bn.eps]
+
+    h = oracle_mod.spconv_gemm(feats, blk.conv1.weight.detach().cpu().numpy(), pair)
+    h = oracle_mod.bn_relu(h, *bn_args(blk.bn1), relu=True)
+    h = oracle_mod.spconv_gemm(h, blk.conv2.weight.detach().cpu().numpy(), pair)
+    ref = oracle_mod.bn_relu(h, *bn_args(blk.bn2), residual=feats, relu=True)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+    # unfused module path (training-mode wiring with eval BN statistics) gives the same values
+    blk.conv1.fuse_epilogue = blk.conv2.fuse_epilogue = False
+    x = tensor_from(idx, feats, shape, batch)
+    with torch.no_grad():
+        o1 = blk.conv1(x)
+        o1 = o1.replace_feature(torch.relu(blk.bn1(o1.features)))
+        o2 = blk.conv2(o1)
+        un = torch.relu(blk.bn2(o2.features) + x.features).cpu().numpy()
+    np.testing.assert_allclose(out, un, rtol=1e-5, atol=1e-5)
+
+
+def _oracle_encoder(oracle_mod, enc, feats, idx, batch):
+    """Walk the module tree of a BEVFusionSparseEncoder and redo every step with the oracle."""
+    shape = list(enc.sparse_shape)
+
+    def bn_args(bn):
+        return [t.detach().cpu().numpy() for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)] + [bn.eps]
+
+    def conv(m, f, i, shp):
+        o_idx, pair, o_shape = oracle_mod.spconv_rulebook(i, shp, m.kernel_size, m.stride, m.padding, m.dilation,
+                                                          m.subm)
+        return oracle_mod.spconv_gemm(f, m.weight.detach().cpu().numpy(), pair), o_idx, [int(v) for v in o_shape]
+
+    def convmodule(seq, f, i, shp):
+        f, i, shp = conv(seq[0], f, i, shp)
+        return oracle_mod.bn_relu(f, *bn_args(seq[1]), relu=True), i, shp
+
+    f, i, shp = convmodule(enc.conv_input, feats, idx, shape)
+    for stage in enc.encoder_layers:
+        for blk in stage:
+            if isinstance(blk, SparseBasicBlock):
+                h, _, _ = conv(blk.conv1, f, i, shp)
+                h = oracle_mod.bn_relu(h, *bn_args(blk.bn1), relu=True)
+                h, _, _ = conv(blk.conv2, h, i, shp)
+                f = oracle_mod.bn_relu(h, *bn_args(blk.bn2), residual=f, relu=True)
+            else:
+                f, i, shp = convmodule(blk, f, i, shp)
+    f, i, shp = convmodule(enc.conv_out, f, i, shp)
+    dense = oracle_mod.sparse_to_dense(f, i, batch, shp)  # [B, C, X, Y, Z]
+    B, C, X, Y, Z = dense.shape
+    return np.ascontiguousarray(dense.transpose(0, 1, 4, 2, 3)).reshape(B, C * Z, X, Y)
+
+
+def _make_encoder(in_channels, sparse_shape, seed):
+    cfg = dict(NUSCENES_ENCODER_CFG)
+    cfg.update(in_channels=in_channels, sparse_shape=sparse_shape)
+    torch.manual_seed(seed)
+    enc = BEVFusionSparseEncoder(**cfg).cuda().eval()
+    g = torch.Generator().manual_seed(seed)
+    for m in enc.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            with torch.no_grad():
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+        elif isinstance(m, spconv.SparseConvolution):
+            with torch.no_grad():
+                fan = m.in_channels * 27
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan) ** 0.5)
+    return enc
+
+
+@pytest.mark.parametrize("in_channels", [5, 3])
+def test_sparse_encoder_matches_oracle_chain(oracle_mod, in_channels):
+    """21-conv BEVFusionSparseEncoder (nuScenes layer list) on a 64 x 64 x 41 grid, batch 2."""
+    rng = np.random.default_rng(in_channels)
+    shape, batch = [64, 64, 41], 2
+    idx = random_sites(rng, 12000, batch, shape)
+    feats = rng.standard_normal((idx.shape[0], in_channels)).astype(np.float32)
+    enc = _make_encoder(in_channels, shape, seed=in_channels)
+    assert sum(isinstance(m, spconv.SparseConvolution) for m in enc.modules()) == 21
+    spconv.set_default_precision("fp32")
+    with torch.no_grad():
+        out = enc(torch.from_numpy(feats).cuda(), torch.from_numpy(idx).cuda(), batch).cpu().numpy()
+    ref = _oracle_encoder(oracle_mod, enc, feats, idx, batch)
+    assert out.shape == ref.shape == (batch, 256, 8, 8)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5 * scale)
+    # bf16 tensor-core path: every layer but conv_input's 5->16 is supported (5 pads to 16)
+    spconv.set_default_precision("bf16")
+    try:
+        with torch.no_grad():
+            out_bf = enc(torch.from_numpy(feats).cuda(), torch.from_numpy(idx).cuda(), batch).cpu().numpy()
+    finally:
+        spconv.set_default_precision("fp32")
+    assert np.abs(out_bf - ref).max() <= 5e-2 * scale  # 21 layers of bf16 rounding compound past 2e-2 per layer
+    assert np.abs(out_bf - ref).mean() <= 5e-3 * scale
+
+
+def test_encoder_full_grid_shapes():
+    """Config A: real voxelizer output on the 1440 x 1440 x 41 grid -> [1, 256, 180, 180]; the dense BEV map is
+    zero exactly where no conv_out site exists."""
+    from bevfusion_3d_object_detection_b200 import ops
+
+    pts = torch.from_numpy(synthetic.lidar_sweeps(n_sweeps=2, seed=4)).cuda()
+    voxels, coors, npv = ops.voxelization(pts, synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, 10, 160000, True)
+    feats = voxels.sum(1) / npv.float().unsqueeze(1)
+    idx = torch.cat([torch.zeros((coors.shape[0], 1), dtype=torch.int32, device="cuda"), coors], 1)
+    enc = _make_encoder(5, [1440, 1440, 41], seed=1)
+    with torch.no_grad():
+        bev = enc(feats, idx, 1)
+    assert bev.shape == (1, 256, 180, 180)
+    assert torch.isfinite(bev).all()
+    assert int((bev != 0).sum()) > 0
+
+
+def test_training_backward_matches_dense_autograd():
+    """SubM conv gradient (features and weight) against autograd through a dense conv3d on a small grid."""
+    rng = np.random.default_rng(3)
+    shape, batch, cin, cout = [8, 7, 6], 1, 4, 6
+    idx = random_sites(rng, 120, batch, shape)
+    feats = rng.standard_normal((idx.shape[0], cin)).astype(np.float32)
+    conv = spconv.SubMConv3d(cin, cout, 3, padding=1, bias=True).cuda()
+    x = torch.from_numpy(feats).cuda().requires_grad_(True)
+    t = spconv.SparseConvTensor(x, torch.from_numpy(idx).cuda(), shape, batch)
+    out = conv(t).features
+    g = torch.from_numpy(rng.standard_normal(out.shape).astype(np.float32)).cuda()
+    out.backward(g)
+    # dense reference
+    xd = torch.from_numpy(feats).cuda().requires_grad_(True)
+    i = torch.from_numpy(idx).cuda().long()
+    dense = torch.zeros((batch, *shape, cin), device="cuda").index_put((i[:, 0], i[:, 1], i[:, 2], i[:, 3]), xd)
+    dense = dense.permute(0, 4, 1, 2, 3)
+    w = conv.weight.detach().clone().requires_grad_(True)
+    od = torch.nn.functional.conv3d(dense, w.permute(0, 4, 1, 2, 3), conv.bias.detach(), padding=1)
+    ref = od.permute(0, 2, 3, 4, 1)[i[:, 0], i[:, 1], i[:, 2], i[:, 3]]
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+    ref.backward(g)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(conv.weight.grad.cpu().numpy(), w.grad.cpu().numpy(), rtol=1e-4, atol=1e-4)
