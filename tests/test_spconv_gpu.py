@@ -319,6 +319,8 @@ def test_encoder_full_grid_shapes():
 
 def test_training_backward_matches_dense_autograd():
     """SubM conv gradient (features and weight) against autograd through a dense conv3d on a small grid."""
+    torch.backends.cudnn.allow_tf32 = False  # the dense checker must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     rng = np.random.default_rng(3)
     shape, batch, cin, cout = [8, 7, 6], 1, 4, 6
     idx = random_sites(rng, 120, batch, shape)
