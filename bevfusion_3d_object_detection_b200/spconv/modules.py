@@ -61,7 +61,19 @@ class SparseModule(nn.Module):
 
 
 def _fold_bn(bn):
-    """eval-mode BatchNorm1d as y = x * scale + shift."""
+    """eval-mode BatchNorm1d as y = x * scale + shift (cached on the module until a parameter / buffer changes)."""
+    key = (bn.running_var._version, bn.running_mean._version, bn.running_var.data_ptr(),
+           None if bn.weight is None else (bn.weight._version, bn.weight.data_ptr()),
+           None if bn.bias is None else (bn.bias._version, bn.bias.data_ptr()), bn.eps)
+    hit = getattr(bn, "_bevf_folded", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    folded = _fold_bn_now(bn)
+    bn._bevf_folded = (key, folded)
+    return folded
+
+
+def _fold_bn_now(bn):
     inv = torch.rsqrt(bn.running_var.float() + bn.eps)
     w = bn.weight.float() if bn.weight is not None else torch.ones_like(inv)
     b = bn.bias.float() if bn.bias is not None else torch.zeros_like(inv)
