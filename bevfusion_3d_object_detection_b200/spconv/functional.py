@@ -22,6 +22,10 @@ def _triple(v):
     return (int(v),) * 3
 
 
+def _pad4(n):
+    return max(4, (int(n) + 3) // 4 * 4)
+
+
 def conv_out_shape(spatial_shape, ksize, stride, padding, dilation):
     out = (ctypes.c_int * 3)()
     lib().bevf_spconv_out_shape(i32_array(spatial_shape), i32_array(ksize), i32_array(stride), i32_array(padding),
@@ -41,13 +45,14 @@ def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
     with torch.cuda.device(dev):
         st = cur_stream(dev)
         if subm:
-            pair = torch.empty((kv, n_in), dtype=torch.int32, device=dev)
+            ld = _pad4(n_in)  # 16-byte aligned rulebook rows: the GEMM producer reads four entries per load
+            pair = torch.empty((kv, ld), dtype=torch.int32, device=dev)
             check(L.bevf_spconv_subm_rulebook(ptr(x.indices), int(n_in), x.batch_size, in_index.shape_c,
                                               i32_array(ksize), i32_array(dilation), ptr(in_index.mem),
                                               ctypes.c_size_t(in_index.nbytes), ptr(in_index.perm), ptr(pair),
-                                              int(n_in), st))
-            return IndicePair(x.indices, pair, n_in, list(x.spatial_shape), in_index, in_index, ksize, (1, 1, 1),
-                              padding, dilation, True)
+                                              int(ld), st))
+            return IndicePair(x.indices, pair[:, :n_in], n_in, list(x.spatial_shape), in_index, in_index, ksize,
+                              (1, 1, 1), padding, dilation, True)
         out_shape = conv_out_shape(x.spatial_shape, ksize, stride, padding, dilation)
         reach = 1
         for k, s in zip(ksize, stride):
@@ -66,11 +71,12 @@ def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
         n_out = int(n_out_dev.item())
         assert n_out <= cap
         out_indices = out_indices[:n_out]
-        pair = torch.empty((kv, max(n_out, 1)), dtype=torch.int32, device=dev)
+        ld = _pad4(n_out)
+        pair = torch.empty((kv, ld), dtype=torch.int32, device=dev)
         check(L.bevf_spconv_strided_rulebook(ptr(out_indices), int(n_out), None, x.batch_size, in_index.shape_c,
                                              i32_array(ksize), i32_array(stride), i32_array(padding),
                                              i32_array(dilation), ptr(in_index.mem), ctypes.c_size_t(in_index.nbytes),
-                                             ptr(in_index.perm), ptr(pair), int(max(n_out, 1)), st))
+                                             ptr(in_index.perm), ptr(pair), int(ld), st))
         out_index = CoordIndex(out_indices, x.batch_size, out_shape, mem=out_mem)
         return IndicePair(out_indices, pair[:, :n_out] if n_out else pair[:, :0], n_out, out_shape, in_index,
                           out_index, ksize, stride, padding, dilation, False)
@@ -142,7 +148,7 @@ def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, preci
             assert fb.shape[1] == cin_pad and fb.dtype == torch.bfloat16
             if want_bf16:
                 out_bf16 = torch.empty((n_out, cout), dtype=torch.bfloat16, device=dev)
-            check(L.bevf_spconv_gemm_bf16(ptr(fb), ptr(weight_packed), ptr(pair_fwd), int(ld), int(n_out), None,
+            check(L.bevf_spconv_gemm_bf16(ptr(fb), int(fb.shape[0]), ptr(weight_packed), ptr(pair_fwd), int(ld), int(n_out), None,
                                           int(kv), int(cin_pad), int(cout), ptr(bias), ptr(bn_scale), ptr(bn_shift),
                                           ptr(residual), int(bool(relu)), ptr(out), ptr(out_bf16), st))
         else:
