@@ -142,6 +142,10 @@ class BEVFusionSparseEncoder(SparseEncoder):
         self.stage_num = len(self.encoder_channels)
         self.fp16_enabled = False
         self.return_middle_feats = return_middle_feats
+        # the voxelizer emits voxels in first-appearance (point) order; the encoder's output is a dense map, so the
+        # row order inside it is free: ascending cell order makes every conv's input rows one contiguous range per
+        # kernel slab (what the tensor-core kernel's halo staging wants) and the level-0 index needs no permutation
+        self.sort_voxels = True
         first_order = ("conv",) if self.order[0] != "conv" else ("conv", "norm", "act")
         self.conv_input = make_sparse_convmodule(in_channels, self.base_channels, 3, norm_cfg=norm_cfg, padding=1,
                                                  indice_key="subm1", conv_type="SubMConv3d", order=first_order)
@@ -155,6 +159,8 @@ class BEVFusionSparseEncoder(SparseEncoder):
         """voxel_features [M, C] fp32, coors [M, 4] (batch, x, y, z) -> [B, C_out * Z_out, X_out, Y_out]."""
         coors = coors.int()
         x = SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size)
+        if self.sort_voxels and coors.shape[0] > 0:
+            x = _sorted_by_cell(x)
         x = self.conv_input(x)
         encode_features = []
         for encoder_layer in self.encoder_layers:
@@ -165,6 +171,22 @@ class BEVFusionSparseEncoder(SparseEncoder):
         if self.return_middle_feats:
             return spatial_features, encode_features
         return spatial_features
+
+
+def _sorted_by_cell(x):
+    """Same sparse tensor with rows in ascending linear (batch, x, y, z) order; reuses the coordinate index."""
+    from .spconv.core import CoordIndex
+
+    index = x.coord_index()
+    n = x.indices.shape[0]
+    if index.perm is None:
+        return x
+    perm = index.perm[:n].long()
+    out = SparseConvTensor(x.features.index_select(0, perm), x.indices.index_select(0, perm), x.spatial_shape,
+                           x.batch_size)
+    out._index = CoordIndex(out.indices, x.batch_size, x.spatial_shape, mem=index.mem)
+    out._sorted_rows = True
+    return out
 
 
 NUSCENES_ENCODER_CFG = dict(  # projects/BEVFusion/configs/nuscenes/bevfusion_lidar_voxel0075...py:56-65
