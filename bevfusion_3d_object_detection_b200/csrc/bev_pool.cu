@@ -346,6 +346,142 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
   }
 }
 
+// ---- fused forward, ray-major (run) form ---------------------------------------------------------------
+// A "run" is a maximal set of frustum points with the same (camera, depth bin, column w), consecutive rows h, and
+// the same BEV cell.  For a level camera all fH rows of one (camera, d, w) fall into one cell, so a run is ~fH
+// points and there are ~N*D*fW runs (62 k at config A instead of 1.8 M points).
+//   phase 1 (ray-major): one warp per run, runs ordered by (camera, w, d): the fH context rows of a pixel column are
+//            read by the D runs of that column back to back and stay in L1 -- the 581 MB of per-point context
+//            gathers the cell-major kernel pulls through L2 become L1 hits.  partial[run, :] = sum_h depth * ctx.
+//   phase 2 (cell-major): out[cell, :] = sum of the cell's 1-3 partial rows in a fixed order (deterministic),
+//            transposed through shared memory into the channel-major output; empty cells are written as zeros.
+template <int NQ>
+__global__ void __launch_bounds__(256)
+    bev_pool_runs_phase1_kernel(const float *__restrict__ depth, const float *__restrict__ ctx,
+                                const int *__restrict__ run_p0, const int *__restrict__ run_len, int n_runs, int D,
+                                int fH, int fW, int C, float *__restrict__ partial) {
+  const int run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (run >= n_runs) return;
+  const int c4 = C >> 2;
+  const int p0 = __ldg(run_p0 + run);
+  const int len = __ldg(run_len + run);
+  const int plane = fH * fW;
+  const int bn = p0 / (D * plane);
+  const int hw = p0 % plane;                       // h0 * fW + w
+  const float4 *ctx4 = reinterpret_cast<const float4 *>(ctx) + ((size_t)bn * plane + hw) * c4;
+  const float *dp = depth + p0;
+  float4 acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // lanes fetch the run's depth values (stride fW) once; rows are then broadcast by shuffle
+  for (int i0 = 0; i0 < len; i0 += 32) {
+    const int cnt = min(32, len - i0);
+    const float my_d = (lane < cnt) ? __ldg(dp + (size_t)(i0 + lane) * fW) : 0.f;
+    int i = 0;
+    for (; i + 4 <= cnt; i += 4) {
+      float dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dv[u] = __shfl_sync(0xffffffffu, my_d, i + u);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int col = lane + 32 * q;
+        if (col < c4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __ldg(ctx4 + (size_t)(i0 + i + u) * fW * c4 + col);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[q].x = fmaf(dv[u], v[u].x, acc[q].x);
+            acc[q].y = fmaf(dv[u], v[u].y, acc[q].y);
+            acc[q].z = fmaf(dv[u], v[u].z, acc[q].z);
+            acc[q].w = fmaf(dv[u], v[u].w, acc[q].w);
+          }
+        }
+      }
+    }
+    for (; i < cnt; ++i) {
+      const float dv = __shfl_sync(0xffffffffu, my_d, i);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int col = lane + 32 * q;
+        if (col < c4) {
+          const float4 v = __ldg(ctx4 + (size_t)(i0 + i) * fW * c4 + col);
+          acc[q].x = fmaf(dv, v.x, acc[q].x);
+          acc[q].y = fmaf(dv, v.y, acc[q].y);
+          acc[q].z = fmaf(dv, v.z, acc[q].z);
+          acc[q].w = fmaf(dv, v.w, acc[q].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int col = lane + 32 * q;
+    if (col < c4) reinterpret_cast<float4 *>(partial)[(size_t)run * c4 + col] = acc[q];
+  }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(kFusedWarps * 32)
+    bev_pool_runs_phase2_kernel(const float *__restrict__ partial, const int *__restrict__ cell_run_starts,
+                                const int *__restrict__ cell_run_ids, const int *__restrict__ icell, int n_int, int C,
+                                int nz, int nx, int ny, int tiles_y, float *__restrict__ out) {
+  extern __shared__ float tile[];  // [C][kTileY + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c4 = C >> 2;
+  const int ty = blockIdx.x % tiles_y;
+  const int line = blockIdx.x / tiles_y;  // (b*nz + z)*nx + x
+  const int y0 = ty * kTileY;
+  const int ycnt = min(kTileY, ny - y0);
+  const int cell0 = line * ny + y0;
+  for (int i = threadIdx.x; i < C * (kTileY + 1); i += blockDim.x) tile[i] = 0.f;
+  int lo = 0, hi = n_int;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(icell + mid) < cell0) lo = mid + 1; else hi = mid;
+  }
+  __syncthreads();
+  const float4 *p4 = reinterpret_cast<const float4 *>(partial);
+  for (int t = lo + warp; t < n_int; t += kFusedWarps) {
+    const int cell = __ldg(icell + t);
+    if (cell >= cell0 + ycnt) break;
+    const int js = __ldg(cell_run_starts + t), je = __ldg(cell_run_starts + t + 1);
+    float4 acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = js; j < je; ++j) {
+      const int run = __ldg(cell_run_ids + j);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int col = lane + 32 * q;
+        if (col < c4) add4(acc[q], __ldg(p4 + (size_t)run * c4 + col));
+      }
+    }
+    const int yy = cell - cell0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int col = lane + 32 * q;
+      if (col < c4) {
+        tile[(col * 4 + 0) * (kTileY + 1) + yy] = acc[q].x;
+        tile[(col * 4 + 1) * (kTileY + 1) + yy] = acc[q].y;
+        tile[(col * 4 + 2) * (kTileY + 1) + yy] = acc[q].z;
+        tile[(col * 4 + 3) * (kTileY + 1) + yy] = acc[q].w;
+      }
+    }
+  }
+  __syncthreads();
+  const int x_ = line % nx;
+  const int bz = line / nx;
+  const int z_ = bz % nz, b_ = bz / nz;
+  for (int ch = warp; ch < C; ch += kFusedWarps) {
+    if (lane < ycnt) {
+      size_t o = ((((size_t)b_ * C + ch) * nz + z_) * nx + x_) * (size_t)ny + y0 + lane;
+      out[o] = tile[ch * (kTileY + 1) + lane];
+    }
+  }
+}
+
 // ---- fused backward --------------------------------------------------------------------------------
 // One warp per pixel (bn, h, w); a CTA takes 8 consecutive w so the 4-byte gathers of cell_of_point / depth
 // at fixed d share 32-byte sectors.  out_grad must be channels-last [cells, C].
@@ -580,6 +716,44 @@ BEVF_API int bevf_bev_pool_fused_forward(const float *depth, const float *ctx_nh
   } else {
     bev_pool_fused_fwd_kernel<2><<<(unsigned)blocks, kFusedWarps * 32, smem, st>>>(
         depth, ctx_nhwc, src, interval_starts, interval_cell, n_int, d, fh * fw, c, nz, nx, ny, tiles_y, out);
+  }
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
+
+BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *ctx_nhwc, const int *run_p0,
+                                              const int *run_len, int n_runs, const int *cell_run_starts,
+                                              const int *cell_run_ids, const int *interval_cell, int n_int, int bn,
+                                              int d, int fh, int fw, int c, int b, int nz, int nx, int ny,
+                                              float *partial, float *out, void *stream) {
+  BEVF_CHECK_ARG(c > 0 && c % 4 == 0 && c <= 256, "C must be a multiple of 4 and <= 256 (got %d)", c);
+  BEVF_CHECK_ARG(bn > 0 && d > 0 && fh > 0 && fw > 0 && b > 0 && nz > 0 && nx > 0 && ny > 0, "bad dims");
+  BEVF_CHECK_ARG((long long)bn * d * fh * fw < (1ll << 31), "frustum has >= 2^31 points");
+  BEVF_CHECK_ARG(n_int >= 0 && n_runs >= 0, "bad table sizes");
+  BEVF_CHECK_ARG(out && depth && ctx_nhwc && (n_runs == 0 || partial), "NULL tensor");
+  BEVF_CHECK_ARG((reinterpret_cast<uintptr_t>(ctx_nhwc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15u) == 0,
+                 "ctx / partial must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_y = bevf::ceil_div(ny, kTileY);
+  const long long blocks = (long long)b * nz * nx * tiles_y;
+  BEVF_CHECK_ARG(blocks < (1ll << 31), "too many output tiles");
+  const size_t smem = (size_t)c * (kTileY + 1) * sizeof(float);
+  const int p1_blocks = bevf::ceil_div((long long)n_runs * 32, 256);
+  if (c / 4 <= 32) {
+    if (n_runs > 0)
+      bev_pool_runs_phase1_kernel<1><<<p1_blocks, 256, 0, st>>>(depth, ctx_nhwc, run_p0, run_len, n_runs, d, fh, fw, c,
+                                                               partial);
+    BEVF_CHECK_LAUNCH();
+    bev_pool_runs_phase2_kernel<1><<<(unsigned)blocks, kFusedWarps * 32, smem, st>>>(
+        partial, cell_run_starts, cell_run_ids, interval_cell, n_int, c, nz, nx, ny, tiles_y, out);
+  } else {
+    if (n_runs > 0)
+      bev_pool_runs_phase1_kernel<2><<<p1_blocks, 256, 0, st>>>(depth, ctx_nhwc, run_p0, run_len, n_runs, d, fh, fw, c,
+                                                               partial);
+    BEVF_CHECK_LAUNCH();
+    bev_pool_runs_phase2_kernel<2><<<(unsigned)blocks, kFusedWarps * 32, smem, st>>>(
+        partial, cell_run_starts, cell_run_ids, interval_cell, n_int, c, nz, nx, ny, tiles_y, out);
   }
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;

@@ -118,9 +118,12 @@ class BevPoolTables:
       interval_starts[n_int+1] int32  CSR offsets into src
       interval_cell  [n_int]   int32  output cell (b*nz+z)*nx*ny + x*ny + y, ascending
       cell_of_point  [N']      int32  output cell of every frustum point or -1 (backward)
+
+    With `frustum_shape=(B*N, D, fH, fW)` the ray-major run tables of the two-phase forward are built as well
+    (run_p0, run_len, cell_run_starts, cell_run_ids; see csrc/bev_pool.cu) and used when runs average >= 4 points.
     """
 
-    def __init__(self, geom_feats, kept, ranks, indices, B, nz, nx, ny):
+    def __init__(self, geom_feats, kept, ranks, indices, B, nz, nx, ny, frustum_shape=None):
         dev = geom_feats.device
         nk = geom_feats.shape[0]
         kept_idx = torch.nonzero(kept.reshape(-1), as_tuple=False).squeeze(1)
@@ -146,6 +149,36 @@ class BevPoolTables:
         cop[src] = cell.int()
         self.cell_of_point = cop
         self.B, self.nz, self.nx, self.ny = int(B), int(nz), int(nx), int(ny)
+        self.use_runs = False
+        self.n_runs = 0
+        if frustum_shape is not None and nk > 0:
+            self._build_runs(src.long(), cell.long(), frustum_shape)
+
+    def _build_runs(self, p, cell, frustum_shape):
+        _, D, fH, fW = [int(v) for v in frustum_shape]
+        plane = fH * fW
+        bn = p // (D * plane)
+        d = (p // plane) % D
+        h = (p // fW) % fH
+        w = p % fW
+        q = ((bn * fW + w) * D + d) * fH + h           # ray-major key: rows h of one (camera, column, depth bin) adjacent
+        q, order = torch.sort(q)
+        cs, ps = cell[order], p[order]
+        first = torch.ones_like(q, dtype=torch.bool)
+        first[1:] = (q[1:] != q[:-1] + 1) | ((q[1:] // fH) != (q[:-1] // fH)) | (cs[1:] != cs[:-1])
+        starts = torch.nonzero(first, as_tuple=False).squeeze(1)
+        n_runs = int(starts.numel())
+        lens = torch.diff(torch.cat([starts, starts.new_tensor([q.numel()])]))
+        run_cell = cs[starts]
+        by_cell = torch.argsort(run_cell, stable=True)
+        cells_u, counts = torch.unique_consecutive(run_cell[by_cell], return_counts=True)
+        assert torch.equal(cells_u.int(), self.interval_cell), "run tables and interval tables disagree on the cell set"
+        self.n_runs = n_runs
+        self.run_p0 = ps[starts].int().contiguous()
+        self.run_len = lens.int().contiguous()
+        self.cell_run_ids = by_cell.int().contiguous()
+        self.cell_run_starts = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)]).int().contiguous()
+        self.use_runs = n_runs * 4 <= self.nk
 
 
 def nchw_to_nhwc(x):
@@ -177,10 +210,17 @@ class _BevPoolFused(torch.autograd.Function):
         t = tables
         out = torch.empty((t.B, c * t.nz, t.nx, t.ny), dtype=torch.float32, device=depth.device)
         with torch.cuda.device(depth.device):
-            check(lib().bevf_bev_pool_fused_forward(ptr(depth), ptr(ctx_nhwc), ptr(t.src), ptr(t.interval_starts),
-                                                    ptr(t.interval_cell), t.n_intervals, t.nk, int(bn), int(d),
-                                                    int(fh), int(fw), int(c), t.B, t.nz, t.nx, t.ny, ptr(out),
-                                                    cur_stream(depth.device)))
+            if t.use_runs:
+                partial = torch.empty((t.n_runs, c), dtype=torch.float32, device=depth.device)
+                check(lib().bevf_bev_pool_fused_forward_runs(
+                    ptr(depth), ptr(ctx_nhwc), ptr(t.run_p0), ptr(t.run_len), t.n_runs, ptr(t.cell_run_starts),
+                    ptr(t.cell_run_ids), ptr(t.interval_cell), t.n_intervals, int(bn), int(d), int(fh), int(fw),
+                    int(c), t.B, t.nz, t.nx, t.ny, ptr(partial), ptr(out), cur_stream(depth.device)))
+            else:
+                check(lib().bevf_bev_pool_fused_forward(ptr(depth), ptr(ctx_nhwc), ptr(t.src), ptr(t.interval_starts),
+                                                        ptr(t.interval_cell), t.n_intervals, t.nk, int(bn), int(d),
+                                                        int(fh), int(fw), int(c), t.B, t.nz, t.nx, t.ny, ptr(out),
+                                                        cur_stream(depth.device)))
         ctx.save_for_backward(depth, ctx_nhwc)
         ctx.tables = tables
         return out

@@ -108,8 +108,9 @@ class BaseViewTransform(nn.Module):
         """Per-calibration tables for `pool_fused` from a geometry tensor [B,N,D,fH,fW,3]."""
         geom_feats, kept, ranks, indices = self.bev_pool_aux(geom)
         B = geom.shape[0] if B is None else B
+        Bg, N, D, fH, fW, _ = geom.shape
         self._tables = BevPoolTables(geom_feats, kept, ranks, indices, B, int(self.nx[2]), int(self.nx[0]),
-                                     int(self.nx[1]))
+                                     int(self.nx[1]), frustum_shape=(Bg * N, D, fH, fW))
         return self._tables
 
     def pool_fused(self, depth, ctx, tables=None):

@@ -129,6 +129,13 @@ def test_fused_forward_matches_reference_chain(oracle_mod, case):
     d_t, c_t = torch.from_numpy(depth).cuda(), torch.from_numpy(ctx).cuda()
     tabs = vt.build_tables(geom)
     out = vt.pool_fused(d_t, c_t)
+    # both forward kernels (ray-major runs, cell-major intervals) must agree; `out` above used the default choice
+    assert tabs.n_runs > 0
+    tabs.use_runs = not tabs.use_runs
+    out_other = vt.pool_fused(d_t, c_t)
+    tabs.use_runs = not tabs.use_runs
+    np.testing.assert_allclose(out_other.cpu().numpy(), out.cpu().numpy(), rtol=RTOL,
+                               atol=RTOL * float(out.abs().max()))
     # (1) against the boundary form fed with the materialised frustum tensor (the reference's own data path)
     x = (d_t.unsqueeze(1) * c_t.unsqueeze(2)).view(B, N, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
     vt.eval()
@@ -145,6 +152,7 @@ def test_fused_forward_matches_reference_chain(oracle_mod, case):
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=RTOL, atol=RTOL * scale)
     if case == "config_A":
         assert tabs.nk > 1_700_000 and 40_000 < tabs.n_intervals < 50_000
+        assert tabs.use_runs and tabs.n_runs < 80_000   # ~N*D*fW runs of ~fH points
 
 
 def test_fused_backward_matches_autograd_of_reference_chain():

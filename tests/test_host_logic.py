@@ -88,3 +88,53 @@ def test_fused_tables_describe_the_same_pooling(oracle_mod):
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
     cop = tabs.cell_of_point.numpy()
     assert (cop >= 0).sum() == tabs.nk and (cop[~kept.numpy()] == -1).all()
+
+
+def test_run_tables_describe_the_same_pooling(oracle_mod):
+    """The ray-major run tables (run_p0 / run_len / cell CSR) partition exactly the kept points and, summed run by
+    run and then cell by cell (what the two-phase kernel does), give the reference chain's BEV map."""
+    vt = _small_vt()
+    rig = {k: torch.from_numpy(v) for k, v in synthetic.camera_rig(n_cams=3, image_size=(64, 96), batch=2,
+                                                                  src_size=(200, 300), resize=0.4).items()}
+    geom = vt.get_geometry(**rig)
+    B, N, D, fH, fW, _ = geom.shape
+    C = 8
+    depth, ctx = synthetic.camera_features(n_cams=N, D=D, C=C, feature_size=(fH, fW), batch=B, seed=5)
+    tabs = vt.build_tables(geom)
+    assert tabs.n_runs > 0 and int(tabs.run_len.sum()) == tabs.nk
+    assert int(tabs.cell_run_starts[-1]) == tabs.n_runs and tabs.cell_run_starts.numel() == tabs.n_intervals + 1
+    plane = fH * fW
+    p0, ln = tabs.run_p0.numpy().astype(np.int64), tabs.run_len.numpy()
+    # every run stays inside one (camera, depth bin, column): rows h0 .. h0+len-1
+    h0 = (p0 // fW) % fH
+    assert (h0 + ln <= fH).all()
+    cop = tabs.cell_of_point.numpy()
+    covered = np.zeros(cop.shape[0], bool)
+    dflat = depth.reshape(-1)
+    ctx_nhwc = np.ascontiguousarray(ctx.transpose(0, 2, 3, 1)).reshape(-1, C)
+    partial = np.zeros((tabs.n_runs, C), np.float64)
+    run_cell = np.zeros(tabs.n_runs, np.int64)
+    for r in range(tabs.n_runs):
+        pts = p0[r] + np.arange(ln[r]) * fW
+        assert not covered[pts].any()
+        covered[pts] = True
+        cells = cop[pts]
+        assert (cells == cells[0]).all() and cells[0] >= 0
+        run_cell[r] = cells[0]
+        pix = (pts // (D * plane)) * plane + pts % plane
+        partial[r] = (dflat[pts][:, None].astype(np.float64) * ctx_nhwc[pix]).sum(0)
+    assert (covered == (cop >= 0)).all()
+    nz, nx, ny = tabs.nz, tabs.nx, tabs.ny
+    out = np.zeros((B * nz * nx * ny, C))
+    starts, ids, icell = tabs.cell_run_starts.numpy(), tabs.cell_run_ids.numpy(), tabs.interval_cell.numpy()
+    for t in range(tabs.n_intervals):
+        rr = ids[starts[t]:starts[t + 1]]
+        assert (run_cell[rr] == icell[t]).all()
+        out[icell[t]] = partial[rr].sum(0)
+    out = out.reshape(B, nz, nx, ny, C).transpose(0, 4, 1, 2, 3).reshape(B, C * nz, nx, ny)
+    # reference chain
+    gf, kept, ranks, indices = vt.bev_pool_aux(geom)
+    src = torch.nonzero(kept, as_tuple=False).squeeze(1)[indices].numpy()
+    st, lg = oracle_mod.intervals_from_ranks(ranks.numpy())
+    ref = oracle_mod.bev_pool_fused(depth, ctx, src, gf.numpy().astype(np.int32), st, lg, B, nz, nx, ny)
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
