@@ -355,70 +355,95 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
 //            gathers the cell-major kernel pulls through L2 become L1 hits.  partial[run, :] = sum_h depth * ctx.
 //   phase 2 (cell-major): out[cell, :] = sum of the cell's 1-3 partial rows in a fixed order (deterministic),
 //            transposed through shared memory into the channel-major output; empty cells are written as zeros.
+// phase 1: one CTA per (pixel column, part).  The column's fH context rows and the depth values of the CTA's depth
+// range are staged in shared memory once; a warp then reduces FOUR runs at a time: one LDS.128 of a context row chunk
+// feeds four accumulators, the depth weights sit in registers (lane = row h) and are broadcast by shuffle.
+constexpr int kRunsPerWarp = 4;
 template <int NQ>
 __global__ void __launch_bounds__(256)
     bev_pool_runs_phase1_kernel(const float *__restrict__ depth, const float *__restrict__ ctx,
-                                const int *__restrict__ run_p0, const int *__restrict__ run_len, int n_runs, int D,
-                                int fH, int fW, int C, float *__restrict__ partial) {
-  const int run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (run >= n_runs) return;
+                                const int *__restrict__ run_p0, const int *__restrict__ run_len,
+                                const int *__restrict__ col_run_starts, int split, int D, int fH, int fW, int C,
+                                float *__restrict__ partial) {
+  extern __shared__ float4 smem4[];
+  const int col = blockIdx.x / split, part = blockIdx.x % split;
+  const int rs = __ldg(col_run_starts + col), re = __ldg(col_run_starts + col + 1);
+  const int chunk = (re - rs + split - 1) / split;
+  const int my_s = rs + part * chunk, my_e = min(re, my_s + chunk);
+  if (my_s >= my_e) return;
   const int c4 = C >> 2;
-  const int p0 = __ldg(run_p0 + run);
-  const int len = __ldg(run_len + run);
   const int plane = fH * fW;
-  const int bn = p0 / (D * plane);
-  const int hw = p0 % plane;                       // h0 * fW + w
-  const float4 *ctx4 = reinterpret_cast<const float4 *>(ctx) + ((size_t)bn * plane + hw) * c4;
-  const float *dp = depth + p0;
-  float4 acc[NQ];
+  const int bn = col / fW, w = col % fW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 *ctx_s = smem4;                                        // [fH][c4]
+  float *depth_s = reinterpret_cast<float *>(smem4 + fH * c4);   // [d_hi - d_lo + 1][fH]
+  const float4 *ctx4 = reinterpret_cast<const float4 *>(ctx);
+  for (int i = threadIdx.x; i < fH * c4; i += blockDim.x) {
+    const int h = i / c4, c = i - h * c4;
+    ctx_s[i] = __ldg(ctx4 + ((size_t)(bn * fH + h) * fW + w) * c4 + c);
+  }
+  const int d_lo = (__ldg(run_p0 + my_s) / plane) % D, d_hi = (__ldg(run_p0 + my_e - 1) / plane) % D;
+  for (int i = threadIdx.x; i < (d_hi - d_lo + 1) * fH; i += blockDim.x) {
+    const int dd = i / fH, h = i - dd * fH;
+    depth_s[i] = __ldg(depth + ((size_t)(bn * D + d_lo + dd) * fH + h) * fW + w);
+  }
+  __syncthreads();
+  for (int q0 = my_s + warp * kRunsPerWarp; q0 < my_e; q0 += (blockDim.x >> 5) * kRunsPerWarp) {
+    int dj[kRunsPerWarp], h0[kRunsPerWarp], h1[kRunsPerWarp];
+    int hmin = fH, hmax = 0;
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // lanes fetch the run's depth values (stride fW) once; rows are then broadcast by shuffle
-  for (int i0 = 0; i0 < len; i0 += 32) {
-    const int cnt = min(32, len - i0);
-    const float my_d = (lane < cnt) ? __ldg(dp + (size_t)(i0 + lane) * fW) : 0.f;
-    int i = 0;
-    for (; i + 4 <= cnt; i += 4) {
-      float dv[4];
+    for (int j = 0; j < kRunsPerWarp; ++j) {
+      dj[j] = 0; h0[j] = 0; h1[j] = 0;
+      if (q0 + j < my_e) {
+        const int p0 = __ldg(run_p0 + q0 + j);
+        dj[j] = (p0 / plane) % D - d_lo;
+        h0[j] = (p0 % plane) / fW;
+        h1[j] = h0[j] + __ldg(run_len + q0 + j);
+        hmin = min(hmin, h0[j]);
+        hmax = max(hmax, h1[j]);
+      }
+    }
+    float4 acc[kRunsPerWarp][NQ];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) dv[u] = __shfl_sync(0xffffffffu, my_d, i + u);
+    for (int j = 0; j < kRunsPerWarp; ++j)
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int col = lane + 32 * q;
-        if (col < c4) {
-          float4 v[4];
+      for (int q = 0; q < NQ; ++q) acc[j][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hb = hmin; hb < hmax; hb += 32) {
+      float wreg[kRunsPerWarp];
+      const int h = hb + lane;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __ldg(ctx4 + (size_t)(i0 + i + u) * fW * c4 + col);
+      for (int j = 0; j < kRunsPerWarp; ++j) wreg[j] = (h >= h0[j] && h < h1[j]) ? depth_s[dj[j] * fH + h] : 0.f;
+      const int cnt = min(32, hmax - hb);
+      for (int i = 0; i < cnt; ++i) {
+        float wj[kRunsPerWarp];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc[q].x = fmaf(dv[u], v[u].x, acc[q].x);
-            acc[q].y = fmaf(dv[u], v[u].y, acc[q].y);
-            acc[q].z = fmaf(dv[u], v[u].z, acc[q].z);
-            acc[q].w = fmaf(dv[u], v[u].w, acc[q].w);
+        for (int j = 0; j < kRunsPerWarp; ++j) wj[j] = __shfl_sync(0xffffffffu, wreg[j], i);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int cc = lane + 32 * q;
+          if (cc < c4) {
+            const float4 v = ctx_s[(hb + i) * c4 + cc];
+#pragma unroll
+            for (int j = 0; j < kRunsPerWarp; ++j) {
+              acc[j][q].x = fmaf(wj[j], v.x, acc[j][q].x);
+              acc[j][q].y = fmaf(wj[j], v.y, acc[j][q].y);
+              acc[j][q].z = fmaf(wj[j], v.z, acc[j][q].z);
+              acc[j][q].w = fmaf(wj[j], v.w, acc[j][q].w);
+            }
           }
         }
       }
     }
-    for (; i < cnt; ++i) {
-      const float dv = __shfl_sync(0xffffffffu, my_d, i);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int col = lane + 32 * q;
-        if (col < c4) {
-          const float4 v = __ldg(ctx4 + (size_t)(i0 + i) * fW * c4 + col);
-          acc[q].x = fmaf(dv, v.x, acc[q].x);
-          acc[q].y = fmaf(dv, v.y, acc[q].y);
-          acc[q].z = fmaf(dv, v.z, acc[q].z);
-          acc[q].w = fmaf(dv, v.w, acc[q].w);
+    for (int j = 0; j < kRunsPerWarp; ++j) {
+      if (q0 + j < my_e) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int cc = lane + 32 * q;
+          if (cc < c4) reinterpret_cast<float4 *>(partial)[(size_t)(q0 + j) * c4 + cc] = acc[j][q];
         }
       }
     }
-  }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int col = lane + 32 * q;
-    if (col < c4) reinterpret_cast<float4 *>(partial)[(size_t)run * c4 + col] = acc[q];
   }
 }
 
@@ -723,36 +748,58 @@ BEVF_API int bevf_bev_pool_fused_forward(const float *depth, const float *ctx_nh
 
 
 BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *ctx_nhwc, const int *run_p0,
-                                              const int *run_len, int n_runs, const int *cell_run_starts,
-                                              const int *cell_run_ids, const int *interval_cell, int n_int, int bn,
-                                              int d, int fh, int fw, int c, int b, int nz, int nx, int ny,
-                                              float *partial, float *out, void *stream) {
+                                              const int *run_len, int n_runs, const int *col_run_starts,
+                                              const int *cell_run_starts, const int *cell_run_ids,
+                                              const int *interval_cell, int n_int, int bn, int d, int fh, int fw,
+                                              int c, int b, int nz, int nx, int ny, float *partial, float *out,
+                                              void *stream) {
   BEVF_CHECK_ARG(c > 0 && c % 4 == 0 && c <= 256, "C must be a multiple of 4 and <= 256 (got %d)", c);
   BEVF_CHECK_ARG(bn > 0 && d > 0 && fh > 0 && fw > 0 && b > 0 && nz > 0 && nx > 0 && ny > 0, "bad dims");
   BEVF_CHECK_ARG((long long)bn * d * fh * fw < (1ll << 31), "frustum has >= 2^31 points");
   BEVF_CHECK_ARG(n_int >= 0 && n_runs >= 0, "bad table sizes");
-  BEVF_CHECK_ARG(out && depth && ctx_nhwc && (n_runs == 0 || partial), "NULL tensor");
+  BEVF_CHECK_ARG(out && depth && ctx_nhwc && (n_runs == 0 || (partial && col_run_starts)), "NULL tensor");
   BEVF_CHECK_ARG((reinterpret_cast<uintptr_t>(ctx_nhwc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15u) == 0,
                  "ctx / partial must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles_y = bevf::ceil_div(ny, kTileY);
   const long long blocks = (long long)b * nz * nx * tiles_y;
   BEVF_CHECK_ARG(blocks < (1ll << 31), "too many output tiles");
-  const size_t smem = (size_t)c * (kTileY + 1) * sizeof(float);
-  const int p1_blocks = bevf::ceil_div((long long)n_runs * 32, 256);
+  const size_t smem2 = (size_t)c * (kTileY + 1) * sizeof(float);
+  // phase 1: columns x parts; enough CTAs to fill the machine a few times over
+  const int n_cols = bn * fw;
+  int split = bevf::ceil_div(4 * bevf::kNumSMs, n_cols);
+  if (split < 1) split = 1;
+  if (split > d) split = d;
+  // depth staging is sized for the whole depth axis: a part's runs may span any depth range (empty bins in between)
+  const size_t smem1 = (size_t)fh * c * sizeof(float) + (size_t)d * fh * sizeof(float);
+  BEVF_CHECK_ARG(smem1 <= 200 * 1024, "pixel column does not fit in shared memory (%zu bytes)", smem1);
   if (c / 4 <= 32) {
-    if (n_runs > 0)
-      bev_pool_runs_phase1_kernel<1><<<p1_blocks, 256, 0, st>>>(depth, ctx_nhwc, run_p0, run_len, n_runs, d, fh, fw, c,
-                                                               partial);
-    BEVF_CHECK_LAUNCH();
-    bev_pool_runs_phase2_kernel<1><<<(unsigned)blocks, kFusedWarps * 32, smem, st>>>(
+    if (n_runs > 0) {
+      static bool configured = false;
+      if (!configured) {
+        BEVF_CHECK_CUDA(cudaFuncSetAttribute(bev_pool_runs_phase1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024));
+        configured = true;
+      }
+      bev_pool_runs_phase1_kernel<1><<<n_cols * split, 256, smem1, st>>>(depth, ctx_nhwc, run_p0, run_len,
+                                                                        col_run_starts, split, d, fh, fw, c, partial);
+      BEVF_CHECK_LAUNCH();
+    }
+    bev_pool_runs_phase2_kernel<1><<<(unsigned)blocks, kFusedWarps * 32, smem2, st>>>(
         partial, cell_run_starts, cell_run_ids, interval_cell, n_int, c, nz, nx, ny, tiles_y, out);
   } else {
-    if (n_runs > 0)
-      bev_pool_runs_phase1_kernel<2><<<p1_blocks, 256, 0, st>>>(depth, ctx_nhwc, run_p0, run_len, n_runs, d, fh, fw, c,
-                                                               partial);
-    BEVF_CHECK_LAUNCH();
-    bev_pool_runs_phase2_kernel<2><<<(unsigned)blocks, kFusedWarps * 32, smem, st>>>(
+    if (n_runs > 0) {
+      static bool configured = false;
+      if (!configured) {
+        BEVF_CHECK_CUDA(cudaFuncSetAttribute(bev_pool_runs_phase1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024));
+        configured = true;
+      }
+      bev_pool_runs_phase1_kernel<2><<<n_cols * split, 256, smem1, st>>>(depth, ctx_nhwc, run_p0, run_len,
+                                                                        col_run_starts, split, d, fh, fw, c, partial);
+      BEVF_CHECK_LAUNCH();
+    }
+    bev_pool_runs_phase2_kernel<2><<<(unsigned)blocks, kFusedWarps * 32, smem2, st>>>(
         partial, cell_run_starts, cell_run_ids, interval_cell, n_int, c, nz, nx, ny, tiles_y, out);
   }
   BEVF_CHECK_LAUNCH();

@@ -176,6 +176,10 @@ class BevPoolTables:
         self.n_runs = n_runs
         self.run_p0 = ps[starts].int().contiguous()
         self.run_len = lens.int().contiguous()
+        col = (self.run_p0.long() // (D * plane)) * fW + self.run_p0.long() % fW
+        n_cols = int(frustum_shape[0]) * fW
+        self.col_run_starts = torch.cat([col.new_zeros(1), torch.cumsum(torch.bincount(col, minlength=n_cols), 0)]
+                                        ).int().contiguous()
         self.cell_run_ids = by_cell.int().contiguous()
         self.cell_run_starts = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)]).int().contiguous()
         self.use_runs = n_runs * 4 <= self.nk
@@ -213,7 +217,8 @@ class _BevPoolFused(torch.autograd.Function):
             if t.use_runs:
                 partial = torch.empty((t.n_runs, c), dtype=torch.float32, device=depth.device)
                 check(lib().bevf_bev_pool_fused_forward_runs(
-                    ptr(depth), ptr(ctx_nhwc), ptr(t.run_p0), ptr(t.run_len), t.n_runs, ptr(t.cell_run_starts),
+                    ptr(depth), ptr(ctx_nhwc), ptr(t.run_p0), ptr(t.run_len), t.n_runs, ptr(t.col_run_starts),
+                    ptr(t.cell_run_starts),
                     ptr(t.cell_run_ids), ptr(t.interval_cell), t.n_intervals, int(bn), int(d), int(fh), int(fw),
                     int(c), t.B, t.nz, t.nx, t.ny, ptr(partial), ptr(out), cur_stream(depth.device)))
             else:

@@ -171,12 +171,14 @@ int bevf_bev_pool_fused_forward(const float *depth, const float *ctx_nhwc, const
  * Same result from the ray-major "run" tables (see bev_pool.cu): a run = points of one (camera, depth bin, column)
  * with consecutive rows h and one BEV cell.
  *   run_p0 [n_runs] int32 frustum index of the run's first point, runs ordered by (camera, w, d, h0);
- *   run_len [n_runs]; cell_run_starts [n_int+1] / cell_run_ids [n_runs]: CSR of the runs of each occupied cell
+ *   run_len [n_runs]; col_run_starts [BN*fW + 1]: CSR of the runs of each pixel column (camera*fW + w);
+ *   cell_run_starts [n_int+1] / cell_run_ids [n_runs]: CSR of the runs of each occupied cell
  *   (interval_cell [n_int], ascending); partial [n_runs, C] fp32 scratch.
  * Two launches; `out` fully written; deterministic (no atomics).
  */
 int bevf_bev_pool_fused_forward_runs(const float *depth, const float *ctx_nhwc, const int *run_p0, const int *run_len,
-                                     int n_runs, const int *cell_run_starts, const int *cell_run_ids,
+                                     int n_runs, const int *col_run_starts, const int *cell_run_starts,
+                                     const int *cell_run_ids,
                                      const int *interval_cell, int n_intervals, int bn, int d, int fh, int fw, int c,
                                      int b, int nz, int nx, int ny, float *partial, float *out, void *stream);
 /*

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_bev_pool_gpu.py -m gpu -q -x -p no:cacheprovider > gpurun_out/t_pool.log 2>&1; echo "pool rc=$?"
-tail -15 gpurun_out/t_pool.log
+tail -5 gpurun_out/t_pool.log
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_bf16.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_bf16.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value']); print(json.dumps(d['stages'],indent=1))"
