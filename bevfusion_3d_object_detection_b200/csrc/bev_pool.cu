@@ -450,8 +450,9 @@ __global__ void __launch_bounds__(256)
 template <int NQ>
 __global__ void __launch_bounds__(kFusedWarps * 32)
     bev_pool_runs_phase2_kernel(const float *__restrict__ partial, const int *__restrict__ cell_run_starts,
-                                const int *__restrict__ cell_run_ids, const int *__restrict__ icell, int n_int, int C,
-                                int nz, int nx, int ny, int tiles_y, float *__restrict__ out) {
+                                const int *__restrict__ cell_run_ids, const int *__restrict__ icell,
+                                const int *__restrict__ tile_starts, int n_int, int C, int nz, int nx, int ny,
+                                int tiles_y, float *__restrict__ out) {
   extern __shared__ float tile[];  // [C][kTileY + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c4 = C >> 2;
@@ -460,15 +461,32 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
   const int y0 = ty * kTileY;
   const int ycnt = min(kTileY, ny - y0);
   const int cell0 = line * ny + y0;
-  for (int i = threadIdx.x; i < C * (kTileY + 1); i += blockDim.x) tile[i] = 0.f;
-  int lo = 0, hi = n_int;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(icell + mid) < cell0) lo = mid + 1; else hi = mid;
+  // first interval of this tile: precomputed per calibration (a 16-step dependent binary search per CTA otherwise)
+  int lo, t_end;
+  if (tile_starts) {
+    lo = __ldg(tile_starts + blockIdx.x);
+    t_end = __ldg(tile_starts + blockIdx.x + 1);
+  } else {
+    lo = 0;
+    int hi = n_int;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (__ldg(icell + mid) < cell0) lo = mid + 1; else hi = mid;
+    }
+    t_end = n_int;
   }
+  const int x_ = line % nx;
+  const int bz = line / nx;
+  const int z_ = bz % nz, b_ = bz / nz;
+  if (tile_starts && lo == t_end) {  // empty tile: nothing to transpose, just the zeros
+    for (int ch = warp; ch < C; ch += kFusedWarps)
+      if (lane < ycnt) out[((((size_t)b_ * C + ch) * nz + z_) * nx + x_) * (size_t)ny + y0 + lane] = 0.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < C * (kTileY + 1); i += blockDim.x) tile[i] = 0.f;
   __syncthreads();
   const float4 *p4 = reinterpret_cast<const float4 *>(partial);
-  for (int t = lo + warp; t < n_int; t += kFusedWarps) {
+  for (int t = lo + warp; t < t_end; t += kFusedWarps) {
     const int cell = __ldg(icell + t);
     if (cell >= cell0 + ycnt) break;
     const int js = __ldg(cell_run_starts + t), je = __ldg(cell_run_starts + t + 1);
@@ -496,15 +514,32 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
     }
   }
   __syncthreads();
-  const int x_ = line % nx;
-  const int bz = line / nx;
-  const int z_ = bz % nz, b_ = bz / nz;
   for (int ch = warp; ch < C; ch += kFusedWarps) {
     if (lane < ycnt) {
       size_t o = ((((size_t)b_ * C + ch) * nz + z_) * nx + x_) * (size_t)ny + y0 + lane;
       out[o] = tile[ch * (kTileY + 1) + lane];
     }
   }
+}
+
+// tile_starts[t] = first interval whose cell lies in or after output tile t (t = line * tiles_y + ty); [n_tiles] = n_int
+__global__ void bev_pool_tile_starts_kernel(const int *__restrict__ icell, int n_int, int ny, int tiles_y,
+                                            long long n_tiles, int *__restrict__ tile_starts) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) {
+    tile_starts[t] = n_int;
+    return;
+  }
+  const long long line = t / tiles_y;
+  const int ty = (int)(t % tiles_y);
+  const long long cell0 = line * ny + (long long)ty * kTileY;
+  int lo = 0, hi = n_int;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(icell + mid) < cell0) lo = mid + 1; else hi = mid;
+  }
+  tile_starts[t] = lo;
 }
 
 // ---- fused backward --------------------------------------------------------------------------------
@@ -747,10 +782,26 @@ BEVF_API int bevf_bev_pool_fused_forward(const float *depth, const float *ctx_nh
 }
 
 
+BEVF_API int bevf_bev_pool_num_tiles(int b, int nz, int nx, int ny) {
+  return (int)((long long)b * nz * nx * bevf::ceil_div(ny, kTileY));
+}
+
+BEVF_API int bevf_bev_pool_tile_starts(const int *interval_cell, int n_int, int b, int nz, int nx, int ny,
+                                       int *tile_starts, void *stream) {
+  BEVF_CHECK_ARG(b > 0 && nz > 0 && nx > 0 && ny > 0 && n_int >= 0 && tile_starts, "bad arguments");
+  const int tiles_y = bevf::ceil_div(ny, kTileY);
+  const long long n_tiles = (long long)b * nz * nx * tiles_y;
+  bev_pool_tile_starts_kernel<<<bevf::ceil_div(n_tiles + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+      interval_cell, n_int, ny, tiles_y, n_tiles, tile_starts);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
 BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *ctx_nhwc, const int *run_p0,
                                               const int *run_len, int n_runs, const int *col_run_starts,
                                               const int *cell_run_starts, const int *cell_run_ids,
-                                              const int *interval_cell, int n_int, int bn, int d, int fh, int fw,
+                                              const int *interval_cell, const int *tile_starts, int n_int, int bn,
+                                              int d, int fh, int fw,
                                               int c, int b, int nz, int nx, int ny, float *partial, float *out,
                                               void *stream) {
   BEVF_CHECK_ARG(c > 0 && c % 4 == 0 && c <= 256, "C must be a multiple of 4 and <= 256 (got %d)", c);
@@ -786,7 +837,7 @@ BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *c
       BEVF_CHECK_LAUNCH();
     }
     bev_pool_runs_phase2_kernel<1><<<(unsigned)blocks, kFusedWarps * 32, smem2, st>>>(
-        partial, cell_run_starts, cell_run_ids, interval_cell, n_int, c, nz, nx, ny, tiles_y, out);
+        partial, cell_run_starts, cell_run_ids, interval_cell, tile_starts, n_int, c, nz, nx, ny, tiles_y, out);
   } else {
     if (n_runs > 0) {
       static bool configured = false;
@@ -800,7 +851,7 @@ BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *c
       BEVF_CHECK_LAUNCH();
     }
     bev_pool_runs_phase2_kernel<2><<<(unsigned)blocks, kFusedWarps * 32, smem2, st>>>(
-        partial, cell_run_starts, cell_run_ids, interval_cell, n_int, c, nz, nx, ny, tiles_y, out);
+        partial, cell_run_starts, cell_run_ids, interval_cell, tile_starts, n_int, c, nz, nx, ny, tiles_y, out);
   }
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;

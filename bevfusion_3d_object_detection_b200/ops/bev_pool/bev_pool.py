@@ -183,6 +183,18 @@ class BevPoolTables:
         self.cell_run_ids = by_cell.int().contiguous()
         self.cell_run_starts = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)]).int().contiguous()
         self.use_runs = n_runs * 4 <= self.nk
+        L = lib()
+        n_tiles = int(L.bevf_bev_pool_num_tiles(self.B, self.nz, self.nx, self.ny))
+        self.tile_starts = torch.empty(n_tiles + 1, dtype=torch.int32, device=p.device)
+        if p.is_cuda:
+            with torch.cuda.device(p.device):
+                check(L.bevf_bev_pool_tile_starts(ptr(self.interval_cell), self.n_intervals, self.B, self.nz, self.nx,
+                                                  self.ny, ptr(self.tile_starts), cur_stream(p.device)))
+        else:  # CPU table build (tests): same table with searchsorted; tiles are 32 cells along y
+            tiles_y = n_tiles // (self.B * self.nz * self.nx)
+            t = torch.arange(n_tiles + 1)
+            cell0 = (t // tiles_y) * self.ny + (t % tiles_y) * 32
+            self.tile_starts = torch.searchsorted(self.interval_cell.long(), cell0).int()
 
 
 def nchw_to_nhwc(x):
@@ -219,7 +231,7 @@ class _BevPoolFused(torch.autograd.Function):
                 check(lib().bevf_bev_pool_fused_forward_runs(
                     ptr(depth), ptr(ctx_nhwc), ptr(t.run_p0), ptr(t.run_len), t.n_runs, ptr(t.col_run_starts),
                     ptr(t.cell_run_starts),
-                    ptr(t.cell_run_ids), ptr(t.interval_cell), t.n_intervals, int(bn), int(d), int(fh), int(fw),
+                    ptr(t.cell_run_ids), ptr(t.interval_cell), ptr(t.tile_starts), t.n_intervals, int(bn), int(d), int(fh), int(fw),
                     int(c), t.B, t.nz, t.nx, t.ny, ptr(partial), ptr(out), cur_stream(depth.device)))
             else:
                 check(lib().bevf_bev_pool_fused_forward(ptr(depth), ptr(ctx_nhwc), ptr(t.src), ptr(t.interval_starts),

@@ -176,10 +176,14 @@ int bevf_bev_pool_fused_forward(const float *depth, const float *ctx_nhwc, const
  *   (interval_cell [n_int], ascending); partial [n_runs, C] fp32 scratch.
  * Two launches; `out` fully written; deterministic (no atomics).
  */
+int bevf_bev_pool_num_tiles(int b, int nz, int nx, int ny);
+/* tile_starts [bevf_bev_pool_num_tiles() + 1]: first interval of every output tile (per calibration; optional). */
+int bevf_bev_pool_tile_starts(const int *interval_cell, int n_intervals, int b, int nz, int nx, int ny, int *tile_starts,
+                              void *stream);
 int bevf_bev_pool_fused_forward_runs(const float *depth, const float *ctx_nhwc, const int *run_p0, const int *run_len,
                                      int n_runs, const int *col_run_starts, const int *cell_run_starts,
                                      const int *cell_run_ids,
-                                     const int *interval_cell, int n_intervals, int bn, int d, int fh, int fw, int c,
+                                     const int *interval_cell, const int *tile_starts, int n_intervals, int bn, int d, int fh, int fw, int c,
                                      int b, int nz, int nx, int ny, float *partial, float *out, void *stream);
 /*
  * Fused backward.  Given the output gradient in channels-last form out_grad_nhwc [B*nz*nx*ny, C]
