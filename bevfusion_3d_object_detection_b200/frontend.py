@@ -60,3 +60,61 @@ class BEVFrontEnd(nn.Module):
     def forward(self, points, depth, ctx, tables=None):
         """-> (lidar_bev [B, 256, 180, 180], camera_bev [B, 80, 360, 360])"""
         return self.extract_pts_feat(points), self.extract_img_bev(depth, ctx, tables)
+
+
+class HostPipeline:
+    """Host-buffer entry point of the front end (what `bench.py` times as `e2e`).
+
+    Pinned host inputs go to the device on a copy-in stream, the front end runs on the compute stream, and both BEV
+    maps return to pinned host buffers on a copy-out stream.  Outputs are `depth`-deep double buffered, so the
+    copies of frame i overlap the compute of frame i+1: steady-state throughput is max(compute, copy), not the sum.
+    """
+
+    def __init__(self, model, tables, device, depth=2):
+        self.model, self.tables, self.device = model, tables, torch.device(device)
+        self.compute = torch.cuda.current_stream(self.device)
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self.slots = [None] * depth          # (lidar_host, cam_host)
+        self.done = [None] * depth           # event: slot's D2H finished
+        self.n = 0
+
+    @torch.no_grad()
+    def submit(self, points, depth, ctx):
+        """points: list of pinned [N_k, C] tensors (one per sample); depth / ctx pinned.  Returns the slot id."""
+        slot = self.n % self.depth
+        self.n += 1
+        with torch.cuda.stream(self.s_in):
+            d_pts = [p.to(self.device, non_blocking=True) for p in points]
+            d_depth = depth.to(self.device, non_blocking=True)
+            d_ctx = ctx.to(self.device, non_blocking=True)
+            e_in = torch.cuda.Event()
+            e_in.record(self.s_in)
+        for t in d_pts + [d_depth, d_ctx]:
+            t.record_stream(self.compute)
+        self.compute.wait_event(e_in)
+        lidar, cam = self.model(d_pts, d_depth, d_ctx, self.tables)
+        e_out = torch.cuda.Event()
+        e_out.record(self.compute)
+        if self.slots[slot] is None:
+            self.slots[slot] = (torch.empty(lidar.shape, dtype=lidar.dtype).pin_memory(),
+                                torch.empty(cam.shape, dtype=cam.dtype).pin_memory())
+        lidar.record_stream(self.s_out)
+        cam.record_stream(self.s_out)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(e_out)
+            self.slots[slot][0].copy_(lidar, non_blocking=True)
+            self.slots[slot][1].copy_(cam, non_blocking=True)
+            self.done[slot] = torch.cuda.Event()
+            self.done[slot].record(self.s_out)
+        return slot
+
+    def result(self, slot):
+        """Blocks until the slot's copies have landed -> (lidar_bev_host, camera_bev_host)."""
+        self.done[slot].synchronize()
+        return self.slots[slot]
+
+    def drain(self):
+        self.s_out.synchronize()
+        self.compute.synchronize()
