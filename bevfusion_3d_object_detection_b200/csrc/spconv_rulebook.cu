@@ -11,6 +11,8 @@
 //     which is this framework's canonical output order (SURVEY 7 "Rulebook bit-exact");
 //   * a level produced by a strided conv needs no row permutation (row == rank), only the raw voxelizer
 //     output (first-appearance order) does.
+#include <cuda_bf16.h>
+
 #include "bitmap_rank.cuh"
 #include "common.cuh"
 
@@ -45,9 +47,12 @@ __device__ __forceinline__ int index_lookup(const IndexView &ix, int b, int x, i
   return ix.perm ? __ldg(ix.perm + rank) : rank;
 }
 
-__global__ void mark_sites_kernel(const int *__restrict__ indices, int n, Grid g, unsigned *__restrict__ bitmap,
-                                  int *__restrict__ error_flag) {
+// every kernel below takes the row count either from the host (n) or, when n_dev != NULL, from device memory
+// (min(*n_dev, n): n is then the capacity the grid was sized for) so a whole frame can run without a host sync
+__global__ void mark_sites_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, Grid g,
+                                  unsigned *__restrict__ bitmap, int *__restrict__ error_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);  // (b, x, y, z)
   if ((unsigned)c.x >= (unsigned)g.b || (unsigned)c.y >= (unsigned)g.x || (unsigned)c.z >= (unsigned)g.y ||
@@ -64,9 +69,11 @@ struct EmitNothing {
   __device__ void operator()(int, unsigned long long) const {}
 };
 
-__global__ void fill_perm_kernel(const int *__restrict__ indices, int n, Grid g, const unsigned *__restrict__ bitmap,
-                                 const int *__restrict__ word_prefix, int *__restrict__ perm) {
+__global__ void fill_perm_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, Grid g,
+                                 const unsigned *__restrict__ bitmap, const int *__restrict__ word_prefix,
+                                 int *__restrict__ perm) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
   if ((unsigned)c.x >= (unsigned)g.b || (unsigned)c.y >= (unsigned)g.x || (unsigned)c.z >= (unsigned)g.y ||
@@ -81,12 +88,13 @@ __global__ void fill_perm_kernel(const int *__restrict__ indices, int n, Grid g,
 // SubM: out sites == in sites; kernel centred; one thread per (site, tap-x/y column), 3..k[2] z-taps share the
 // bitmap word most of the time.
 __global__ void __launch_bounds__(256)
-    subm_rulebook_kernel(const int *__restrict__ indices, int n, IndexView ix, ConvGeom cg, int ld,
-                         int *__restrict__ pair_fwd) {
+    subm_rulebook_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, IndexView ix,
+                         ConvGeom cg, int ld, int *__restrict__ pair_fwd) {
   const int kxy = cg.k[0] * cg.k[1];
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * kxy) return;
   const int j = (int)(t % n);  // consecutive threads -> consecutive sites: coalesced pair_fwd stores
+  if (n_dev && j >= *n_dev) return;
   const int col = (int)(t / n);
   const int kx = col / cg.k[1], ky = col % cg.k[1];
   const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + j);
@@ -101,8 +109,10 @@ __global__ void __launch_bounds__(256)
 
 // strided conv, pass 1: every input marks the output sites it reaches
 __global__ void __launch_bounds__(256)
-    strided_mark_kernel(const int *__restrict__ indices, int n, ConvGeom cg, Grid og, unsigned *__restrict__ out_bitmap) {
+    strided_mark_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom cg, Grid og,
+                        unsigned *__restrict__ out_bitmap) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
   for (int kx = 0; kx < cg.k[0]; ++kx) {
@@ -167,9 +177,10 @@ __global__ void __launch_bounds__(256)
 
 // SparseConvTensor.dense(): [B, C, X, Y, Z]; one thread per (site, channel), channel fastest in the read
 __global__ void __launch_bounds__(256)
-    to_dense_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n, int c, Grid g,
-                    float *__restrict__ dense) {
+    to_dense_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n,
+                    const int *__restrict__ n_dev, int c, Grid g, float *__restrict__ dense) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (t >= (long long)n * c) return;
   const int i = (int)(t / c), ch = (int)(t % c);
   const int4 q = __ldg(reinterpret_cast<const int4 *>(indices) + i);
@@ -180,13 +191,34 @@ __global__ void __launch_bounds__(256)
 // BEVFusionSparseEncoder tail (sparse_encoder.py:147-151): dense() [N,C,X,Y,Z] -> permute(0,1,4,2,3) ->
 // view(N, C*Z, X, Y), fused: bev[b, ch*Z + z, x, y]
 __global__ void __launch_bounds__(256)
-    to_bev_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n, int c, Grid g,
-                  float *__restrict__ bev) {
+    to_bev_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n,
+                  const int *__restrict__ n_dev, int c, Grid g, float *__restrict__ bev) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (t >= (long long)n * c) return;
   const int i = (int)(t / c), ch = (int)(t % c);
   const int4 q = __ldg(reinterpret_cast<const int4 *>(indices) + i);
   bev[((((size_t)q.x * c + ch) * g.z + q.w) * g.x + q.y) * g.y + q.z] = feats[t];
+}
+
+// rows re-ordered by perm (rank -> row): out_indices[r] = indices[perm[r]], features copied as fp32 and/or as bf16
+// zero-padded to cin_pad columns (the tensor-core operand of the first conv)
+__global__ void __launch_bounds__(256)
+    permute_rows_kernel(const float *__restrict__ feats, const int *__restrict__ indices, const int *__restrict__ perm,
+                        int n, const int *__restrict__ n_dev, int c, int cin_pad, int width, float *__restrict__ out_f32,
+                        unsigned short *__restrict__ out_bf16, int *__restrict__ out_indices) {
+  if (n_dev) n = min(n, *n_dev);
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * width) return;
+  const int r = (int)(t / width), col = (int)(t % width);
+  const int src = __ldg(perm + r);
+  if (col < 4) out_indices[(size_t)r * 4 + col] = __ldg(indices + (size_t)src * 4 + col);
+  const float v = col < c ? __ldg(feats + (size_t)src * c + col) : 0.f;
+  if (out_f32 && col < c) out_f32[(size_t)r * c + col] = v;
+  if (out_bf16 && col < cin_pad) {
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    out_bf16[(size_t)r * cin_pad + col] = *reinterpret_cast<unsigned short *>(&b);
+  }
 }
 
 struct IndexMem {
@@ -253,8 +285,8 @@ BEVF_API size_t bevf_spconv_index_bytes(int batch, const int *shape) {
   return carve_index(m, nullptr, 0, nwords) + 256;
 }
 
-BEVF_API int bevf_spconv_index_build(const int *indices, int n, int batch, const int *shape, void *index_mem,
-                                     size_t index_bytes, int *perm, void *stream) {
+BEVF_API int bevf_spconv_index_build(const int *indices, int n, const int *n_dev, int batch, const int *shape,
+                                     void *index_mem, size_t index_bytes, int *perm, void *stream) {
   long long nwords;
   int rc = grid_words(batch, shape, nwords);
   if (rc) return rc;
@@ -271,13 +303,13 @@ BEVF_API int bevf_spconv_index_build(const int *indices, int n, int batch, const
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
   if (n > 0) {
-    mark_sites_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, g, m.bitmap, m.scalars + 1);
+    mark_sites_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, n_dev, g, m.bitmap, m.scalars + 1);
     BEVF_CHECK_LAUNCH();
   }
   rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitNothing{}, st);
   if (rc) return rc;
   if (perm && n > 0) {
-    fill_perm_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, g, m.bitmap, m.word_prefix, perm);
+    fill_perm_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, n_dev, g, m.bitmap, m.word_prefix, perm);
     BEVF_CHECK_LAUNCH();
   }
   return BEVF_OK;
@@ -292,7 +324,8 @@ BEVF_API const int *bevf_spconv_index_error_flag(void *index_mem, size_t index_b
   return m.scalars + 1;
 }
 
-BEVF_API int bevf_spconv_subm_rulebook(const int *indices, int n, int batch, const int *shape, const int *ksize,
+BEVF_API int bevf_spconv_subm_rulebook(const int *indices, int n, const int *n_dev, int batch, const int *shape,
+                                       const int *ksize,
                                        const int *dilation, const void *index_mem, size_t index_bytes,
                                        const int *perm, int *pair_fwd, int ld, void *stream) {
   int rc = check_geom(ksize, nullptr, nullptr, dilation);
@@ -308,13 +341,14 @@ BEVF_API int bevf_spconv_subm_rulebook(const int *indices, int n, int batch, con
   ConvGeom cg;
   fill_geom(cg, ksize, nullptr, nullptr, dilation);
   long long threads = (long long)n * ksize[0] * ksize[1];
-  subm_rulebook_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, ix, cg, ld,
+  subm_rulebook_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, n_dev, ix, cg, ld,
                                                                                         pair_fwd);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;
 }
 
-BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, int batch, const int *in_shape,
+BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, const int *n_in_dev, int batch,
+                                       const int *in_shape,
                                        const int *ksize, const int *stride, const int *padding, const int *dilation,
                                        void *out_index_mem, size_t out_index_bytes, int *out_indices, int cap,
                                        int *n_out_dev, void *stream) {
@@ -338,7 +372,7 @@ BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, int batc
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
   if (n_in > 0) {
-    strided_mark_kernel<<<bevf::ceil_div(n_in, 256), 256, 0, st>>>(in_indices, n_in, cg, og, m.bitmap);
+    strided_mark_kernel<<<bevf::ceil_div(n_in, 256), 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
     BEVF_CHECK_LAUNCH();
   }
   rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitSites{og, out_indices, cap},
@@ -373,8 +407,8 @@ BEVF_API int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, con
   return BEVF_OK;
 }
 
-BEVF_API int bevf_sparse_to_dense(const float *feats, const int *indices, int n, int c, int batch, const int *shape,
-                                  float *dense, int bev_layout, void *stream) {
+BEVF_API int bevf_sparse_to_dense(const float *feats, const int *indices, int n, const int *n_dev, int c, int batch,
+                                  const int *shape, float *dense, int bev_layout, void *stream) {
   BEVF_CHECK_ARG(batch > 0 && c > 0 && n >= 0, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   size_t total = (size_t)batch * c * shape[0] * shape[1] * shape[2];
@@ -382,8 +416,24 @@ BEVF_API int bevf_sparse_to_dense(const float *feats, const int *indices, int n,
   if (n == 0) return BEVF_OK;
   Grid g{batch, shape[0], shape[1], shape[2]};
   long long threads = (long long)n * c;
-  if (bev_layout) to_bev_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, c, g, dense);
-  else to_dense_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, c, g, dense);
+  if (bev_layout) to_bev_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, n_dev, c, g, dense);
+  else to_dense_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, n_dev, c, g, dense);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_spconv_permute_rows(const float *feats, const int *indices, const int *perm, int n, const int *n_dev,
+                                      int c, int cin_pad, float *out_f32, void *out_bf16, int *out_indices,
+                                      void *stream) {
+  BEVF_CHECK_ARG(n >= 0 && c > 0, "bad shapes");
+  BEVF_CHECK_ARG(out_bf16 == nullptr || cin_pad >= c, "cin_pad %d does not cover the %d feature columns", cin_pad, c);
+  if (n == 0) return BEVF_OK;
+  BEVF_CHECK_ARG(feats && indices && perm && out_indices, "NULL tensor");
+  int width = c > 4 ? c : 4;
+  if (out_bf16 && cin_pad > width) width = cin_pad;
+  const long long threads = (long long)n * width;
+  permute_rows_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+      feats, indices, perm, n, n_dev, c, out_bf16 ? cin_pad : 0, width, out_f32, (unsigned short *)out_bf16, out_indices);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;
 }

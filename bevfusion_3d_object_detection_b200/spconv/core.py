@@ -31,7 +31,7 @@ class CoordIndex:
         n = indices.shape[0]
         self.perm = None if sorted_rows else torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            check(L.bevf_spconv_index_build(ptr(indices), int(n), self.batch_size, self.shape_c, ptr(self.mem),
+            check(L.bevf_spconv_index_build(ptr(indices), int(n), None, self.batch_size, self.shape_c, ptr(self.mem),
                                             ctypes.c_size_t(self.nbytes), ptr(self.perm), cur_stream(dev)))
 
     def error_code(self):
@@ -141,7 +141,7 @@ class SparseConvTensor:
         shape = (self.batch_size, c * Z, X, Y) if bev_layout else (self.batch_size, c, X, Y, Z)
         out = torch.empty(shape, dtype=torch.float32, device=f.device)
         with torch.cuda.device(f.device):
-            check(lib().bevf_sparse_to_dense(ptr(f), ptr(self.indices), int(n), int(c), self.batch_size,
+            check(lib().bevf_sparse_to_dense(ptr(f), ptr(self.indices), int(n), None, int(c), self.batch_size,
                                              i32_array(self.spatial_shape), ptr(out), int(bev_layout),
                                              cur_stream(f.device)))
         return out

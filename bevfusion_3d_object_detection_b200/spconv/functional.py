@@ -47,7 +47,7 @@ def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
         if subm:
             ld = _pad4(n_in)  # 16-byte aligned rulebook rows: the GEMM producer reads four entries per load
             pair = torch.empty((kv, ld), dtype=torch.int32, device=dev)
-            check(L.bevf_spconv_subm_rulebook(ptr(x.indices), int(n_in), x.batch_size, in_index.shape_c,
+            check(L.bevf_spconv_subm_rulebook(ptr(x.indices), int(n_in), None, x.batch_size, in_index.shape_c,
                                               i32_array(ksize), i32_array(dilation), ptr(in_index.mem),
                                               ctypes.c_size_t(in_index.nbytes), ptr(in_index.perm), ptr(pair),
                                               int(ld), st))
@@ -65,7 +65,7 @@ def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
         out_mem = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
         out_indices = torch.empty((cap, 4), dtype=torch.int32, device=dev)
         n_out_dev = torch.empty(1, dtype=torch.int32, device=dev)
-        check(L.bevf_spconv_strided_sites(ptr(x.indices), int(n_in), x.batch_size, in_index.shape_c, i32_array(ksize),
+        check(L.bevf_spconv_strided_sites(ptr(x.indices), int(n_in), None, x.batch_size, in_index.shape_c, i32_array(ksize),
                                           i32_array(stride), i32_array(padding), i32_array(dilation), ptr(out_mem),
                                           ctypes.c_size_t(out_bytes), ptr(out_indices), int(cap), ptr(n_out_dev), st))
         n_out = int(n_out_dev.item())

@@ -208,6 +208,9 @@ int bevf_nhwc_to_nchw(const float *src, float *dst, int n, int c, int hw, void *
  * mmdet3d/models/layers/sparse_block.py:201-217, projects/BEVFusion/bevfusion/sparse_encoder.py:131-147;
  * functional boundary documented by projects/SparseConvolution/sparse_functional.py:70-162, 220-320).
  *
+ * Row counts: every function takes the row count as a host int `n`; where a `const int *n_dev` follows it, a non-NULL
+ * pointer makes the kernels use min(*n_dev, n) read on the device (n is then the buffer capacity the grid is sized
+ * for), so a whole frame can be enqueued -- or captured into a CUDA graph -- without a host synchronisation.
  * Conventions: indices [n,4] int32 = (batch, x, y, z), 16-byte aligned; spatial shape (X, Y, Z); kernel taps
  * row-major over (kx, ky, kz) = the (kD,kH,kW) axes of the weight W[Cout, kD, kH, kW, Cin]; cross-correlation
  * out[o] = sum_k W[:,k,:] . in[o*stride - pad + k*dil]; SubM: out sites == in sites (same order), kernel
@@ -228,12 +231,13 @@ int bevf_spconv_out_shape(const int *shape_host, const int *ksize_host, const in
  * grid, 2 duplicate coordinate.
  */
 size_t bevf_spconv_index_bytes(int batch, const int *shape_host);
-int bevf_spconv_index_build(const int *indices, int n, int batch, const int *shape_host, void *index_mem,
-                            size_t index_bytes, int *perm, void *stream);
+int bevf_spconv_index_build(const int *indices, int n, const int *n_dev, int batch, const int *shape_host,
+                            void *index_mem, size_t index_bytes, int *perm, void *stream);
 const int *bevf_spconv_index_error_flag(void *index_mem, size_t index_bytes, int batch, const int *shape_host);
 
 /* SubM rulebook: pair_fwd[k, j] = row of the input at indices[j] + (k - ksize/2) * dilation, or -1. */
-int bevf_spconv_subm_rulebook(const int *indices, int n, int batch, const int *shape_host, const int *ksize_host,
+int bevf_spconv_subm_rulebook(const int *indices, int n, const int *n_dev, int batch, const int *shape_host,
+                              const int *ksize_host,
                               const int *dilation_host, const void *index_mem, size_t index_bytes,
                               const int *perm, int *pair_fwd, int ld, void *stream);
 
@@ -243,7 +247,8 @@ int bevf_spconv_subm_rulebook(const int *indices, int n, int batch, const int *s
  * in ascending linear order and n_out to *n_out_dev.  cap = rows available in out_indices
  * (n_in * min(kv, prod(ceil(k/s))) always suffices).
  */
-int bevf_spconv_strided_sites(const int *in_indices, int n_in, int batch, const int *in_shape_host,
+int bevf_spconv_strided_sites(const int *in_indices, int n_in, const int *n_in_dev, int batch,
+                              const int *in_shape_host,
                               const int *ksize_host, const int *stride_host, const int *padding_host,
                               const int *dilation_host, void *out_index_mem, size_t out_index_bytes,
                               int *out_indices, int cap, int *n_out_dev, void *stream);
@@ -256,8 +261,12 @@ int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, const int *n
 
 /* SparseConvTensor.dense(): dense[B, C, X, Y, Z] (bev_layout == 0) or the BEVFusionSparseEncoder tail
  * (sparse_encoder.py:147-151) dense().permute(0,1,4,2,3).view(B, C*Z, X, Y) (bev_layout != 0).  Fully written. */
-int bevf_sparse_to_dense(const float *feats, const int *indices, int n, int c, int batch, const int *shape_host,
-                         float *dense, int bev_layout, void *stream);
+int bevf_sparse_to_dense(const float *feats, const int *indices, int n, const int *n_dev, int c, int batch,
+                         const int *shape_host, float *dense, int bev_layout, void *stream);
+/* Rows re-ordered by perm (rank -> row, from bevf_spconv_index_build): out_indices[r] = indices[perm[r]]; features
+ * copied as fp32 (out_f32 [n, c], optional) and / or as bf16 zero-padded to cin_pad columns (out_bf16, optional). */
+int bevf_spconv_permute_rows(const float *feats, const int *indices, const int *perm, int n, const int *n_dev, int c,
+                             int cin_pad, float *out_f32, void *out_bf16, int *out_indices, void *stream);
 
 /*
  * Gather-GEMM-scatter (replaces ConvGemmOps.implicit_gemm).  out[j, :] = epilogue(sum_k feats[pair_fwd[k,j], :]
