@@ -42,6 +42,7 @@ class _Level:
         self.index_mem = torch.empty(self.index_bytes, dtype=torch.uint8, device=dev)
         self.subm_pairs = {}   # (ksize, dilation) -> pair_fwd [kv, ld]
         self.subm_fresh = set()
+        self.hint = 0          # expected active rows (tile-shape hint for the GEMM launches; 0 = unknown)
 
 
 class StaticFrontEnd:
@@ -81,7 +82,6 @@ class StaticFrontEnd:
         self.depth = None
         self.ctx = None
         self.graph = None
-        self.lidar_bev = None
         self.cam_bev = None
 
     # ------------------------------------------------------------------------------------------------------------
@@ -243,12 +243,12 @@ class StaticFrontEnd:
             w = conv._packed_weight(self.precision)
             if self.precision == "bf16":
                 cin_pad = int(L.bevf_spconv_tc_cin_pad(conv.in_channels))
-                check(L.bevf_spconv_gemm_bf16(ptr(cur["bf16"]), lin.cap, ptr(w), ptr(pair), lout.ld, lout.cap,
+                check(L.bevf_spconv_gemm_bf16(ptr(cur["bf16"]), lin.cap, ptr(w), ptr(pair), lout.ld, lout.hint,
                                               ptr(lout.n_dev), kv, cin_pad, conv.out_channels, ptr(conv.bias),
                                               ptr(op["scale"]), ptr(op["shift"]), ptr(residual), int(op["relu"]),
                                               ptr(out["f32"]), ptr(out["bf16"]), st))
             else:
-                check(L.bevf_spconv_gemm_f32(ptr(cur["f32"]), ptr(w), ptr(pair), lout.ld, lout.cap, ptr(lout.n_dev), kv,
+                check(L.bevf_spconv_gemm_f32(ptr(cur["f32"]), ptr(w), ptr(pair), lout.ld, lout.hint, ptr(lout.n_dev), kv,
                                              conv.in_channels, conv.out_channels, ptr(conv.bias), ptr(op["scale"]),
                                              ptr(op["shift"]), ptr(residual), int(op["relu"]), ptr(out["f32"]), st))
             if op["residual"] == "block_in":
@@ -279,8 +279,10 @@ class StaticFrontEnd:
         return self.lidar_bev, self.cam_bev
 
     @torch.no_grad()
-    def capture(self):
-        """Capture the frame into a CUDA graph (after one eager warm-up so every kernel attribute is set)."""
+    def capture(self, calibrate=True):
+        """Capture the frame into a CUDA graph.  One eager warm-up first (kernel attributes get set outside the
+        capture); with `calibrate` its per-level site counts (one host sync, once) become the tile-shape hints of
+        the captured GEMM launches.  Load a representative frame before calling."""
         with torch.cuda.device(self.dev):
             side = torch.cuda.Stream(self.dev)
             side.wait_stream(torch.cuda.current_stream(self.dev))
@@ -288,6 +290,9 @@ class StaticFrontEnd:
                 self._enqueue()
             torch.cuda.current_stream(self.dev).wait_stream(side)
             torch.cuda.synchronize(self.dev)
+            if calibrate:
+                for lv, n in zip(self.levels, self.counts()):
+                    lv.hint = min(int(n), lv.cap)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue()

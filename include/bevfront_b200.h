@@ -272,7 +272,8 @@ int bevf_spconv_permute_rows(const float *feats, const int *indices, const int *
  * Gather-GEMM-scatter (replaces ConvGemmOps.implicit_gemm).  out[j, :] = epilogue(sum_k feats[pair_fwd[k,j], :]
  * @ W[k]) with the optional fused epilogue v = acc + bias; v = v*bn_scale + bn_shift; v += residual[j];
  * v = max(v, 0)  (what mmdet3d/models/layers/sparse_block.py:137-154 applies after every conv in eval mode).
- * n_out rows are computed; with n_out_dev != NULL the row count is read from the device (<= ld).
+ * n_out rows are computed; with n_out_dev != NULL the row count is read from the device (<= ld) and the host
+ * n_out is only a hint (expected rows, may be 0 = unknown) for the tile-shape choice.
  *
  * fp32 (parity path, FFMA): weights repacked once to [kv, Cin, Cout] with bevf_spconv_pack_weight_f32 from the
  * spconv-2.x parameter layout [Cout, kD, kH, kW, Cin].
