@@ -49,13 +49,15 @@ class SparseBasicBlock(SparseModule):
         return getattr(self, self.norm2_name)
 
     def forward(self, x):
-        identity = x.features
-        assert x.features.dim() == 2, f"x.features.dim()={x.features.dim()}"
         if self.downsample is None and bn_is_foldable(self.norm1) and bn_is_foldable(self.norm2):
             s1, b1 = _fold_bn(self.norm1)
             s2, b2 = _fold_bn(self.norm2)
+            # the skip connection reads whichever copy of the block input exists (fp32, else the bf16 operand copy)
+            identity = x._features if x._features is not None else x._bf16
             out = self.conv1(x, bn_scale=s1, bn_shift=b1, relu=True)
             return self.conv2(out, bn_scale=s2, bn_shift=b2, residual=identity, relu=True)
+        identity = x.features
+        assert x.features.dim() == 2, f"x.features.dim()={x.features.dim()}"
         out = self.conv1(x)
         out = replace_feature(out, self.norm1(out.features))
         out = replace_feature(out, self.relu(out.features))
@@ -154,6 +156,11 @@ class BEVFusionSparseEncoder(SparseEncoder):
         self.conv_out = make_sparse_convmodule(encoder_out_channels, self.output_channels, kernel_size=(1, 1, 3),
                                                stride=(1, 1, 2), norm_cfg=norm_cfg, padding=0,
                                                indice_key="spconv_down2", conv_type="SparseConv3d")
+        # on the tensor-core path only the last conv's fp32 output is consumed (by dense()); the inner layers hand
+        # their bf16 operand copy to the next conv and to the skip connections
+        for m in self.modules():
+            if hasattr(m, "need_f32") and m is not self.conv_out[0]:
+                m.need_f32 = False
 
     def forward(self, voxel_features, coors, batch_size):
         """voxel_features [M, C] fp32, coors [M, 4] (batch, x, y, z) -> [B, C_out * Z_out, X_out, Y_out]."""

@@ -96,6 +96,8 @@ class SparseConvolution(SparseModule):
         self.name = name
         self.precision = precision      # None -> module default
         self.fuse_epilogue = True       # SparseSequential may fold eval BatchNorm1d + ReLU into this conv
+        self.need_f32 = True            # False: on the tensor-core path write only the bf16 copy (the encoder sets
+                                        # this on its inner layers; `.features` is then materialised on demand)
         self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
         if bias:
             self.bias = nn.Parameter(torch.empty(out_channels))
@@ -171,7 +173,8 @@ class SparseConvolution(SparseModule):
 
     def forward(self, input, bn_scale=None, bn_shift=None, residual=None, relu=False):
         assert isinstance(input, SparseConvTensor)
-        assert input.features.shape[1] == self.in_channels, "channel size mismatch"
+        in_ch = input._features.shape[1] if input._features is not None else self.in_channels
+        assert in_ch == self.in_channels, "channel size mismatch"
         precision = self._resolve_precision()
         datas = self._rulebook(input)
         out = input.shadow_copy()
@@ -182,7 +185,8 @@ class SparseConvolution(SparseModule):
             out._index = datas.out_index
             out._sorted_rows = True
         n_out = datas.n_out
-        needs_grad = torch.is_grad_enabled() and (input.features.requires_grad or self.weight.requires_grad)
+        needs_grad = torch.is_grad_enabled() and (self.weight.requires_grad or (
+            input._features is not None and input._features.requires_grad))
         fused = bn_scale is not None or residual is not None or relu
         if needs_grad:
             assert not fused, "fused BN/ReLU epilogues are inference-only"
@@ -190,10 +194,13 @@ class SparseConvolution(SparseModule):
                                               self._packed_weight(precision), precision)
         else:
             kv = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
-            feats, fb = Fsp.implicit_gemm(input.features, datas.pair_fwd, n_out, self._packed_weight(precision), kv,
-                                          self.in_channels, self.out_channels, precision=precision,
-                                          bias=self.bias, bn_scale=bn_scale, bn_shift=bn_shift, residual=residual,
-                                          relu=relu, features_bf16=input._bf16, want_bf16=(precision == "bf16"))
+            use_bf16_in = precision == "bf16" and input._bf16 is not None
+            feats, fb = Fsp.implicit_gemm(None if use_bf16_in else input.features, datas.pair_fwd, n_out,
+                                          self._packed_weight(precision), kv, self.in_channels, self.out_channels,
+                                          precision=precision, bias=self.bias, bn_scale=bn_scale, bn_shift=bn_shift,
+                                          residual=residual, relu=relu,
+                                          features_bf16=input._bf16 if use_bf16_in else None,
+                                          want_bf16=(precision == "bf16"), want_f32=self.need_f32)
             out._bf16 = fb
         out._features = feats
         return out

@@ -88,6 +88,10 @@ class SparseConvTensor:
     # ---- spconv surface ---------------------------------------------------------------------------------
     @property
     def features(self):
+        # a tensor-core layer that was told not to write fp32 (need_f32 = False) leaves only the bf16 copy; the
+        # fp32 view is materialised on first access
+        if self._features is None and self._bf16 is not None:
+            self._features = self._bf16.float()
         return self._features
 
     @features.setter
@@ -135,7 +139,7 @@ class SparseConvTensor:
 
     # ---- internals --------------------------------------------------------------------------------------
     def _to_dense(self, bev_layout):
-        f = self._features.contiguous().float()
+        f = self.features.contiguous().float()
         n, c = f.shape
         X, Y, Z = self.spatial_shape
         shape = (self.batch_size, c * Z, X, Y) if bev_layout else (self.batch_size, c, X, Y, Z)
@@ -152,4 +156,5 @@ class SparseConvTensor:
         return self._index
 
     def __repr__(self):
-        return f"SparseConvTensor[shape={tuple(self._features.shape)}]"
+        src = self._features if self._features is not None else self._bf16
+        return f"SparseConvTensor[shape={tuple(src.shape)}]"

@@ -120,15 +120,22 @@ def tc_supported(cin, cout):
 
 
 def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, precision="fp32", bias=None, bn_scale=None,
-                  bn_shift=None, residual=None, relu=False, features_bf16=None, want_bf16=False):
-    """out[n_out, Cout] fp32 (and optionally its bf16 copy) = epilogue(sum_k feats[pair_fwd[k]] @ W[k])."""
+                  bn_shift=None, residual=None, relu=False, features_bf16=None, want_bf16=False, want_f32=True):
+    """out[n_out, Cout] fp32 (and optionally its bf16 copy) = epilogue(sum_k feats[pair_fwd[k]] @ W[k]).
+    `residual` may be fp32 or (tensor-core path) bf16.  want_f32=False (tensor-core path only) skips the fp32 output."""
     dev = pair_fwd.device
     L = lib()
-    out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
+    want_f32 = want_f32 or precision != "bf16" or not want_bf16
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=dev) if want_f32 else None
     out_bf16 = None
     ld = pair_fwd.stride(0) if pair_fwd.shape[1] > 0 else max(n_out, 1)
+    residual_bf16 = None
     if residual is not None:
-        residual = residual.contiguous().float()
+        if residual.dtype == torch.bfloat16 and precision == "bf16":
+            residual_bf16, residual = residual.contiguous(), None
+            assert residual_bf16.shape[1] == cout
+        else:
+            residual = residual.contiguous().float()
     timing = GEMM_TIMING
     if timing is not None:
         pairs = int((pair_fwd[:, :n_out] >= 0).sum().item())
@@ -150,7 +157,8 @@ def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, preci
                 out_bf16 = torch.empty((n_out, cout), dtype=torch.bfloat16, device=dev)
             check(L.bevf_spconv_gemm_bf16(ptr(fb), int(fb.shape[0]), ptr(weight_packed), ptr(pair_fwd), int(ld), int(n_out), None,
                                           int(kv), int(cin_pad), int(cout), ptr(bias), ptr(bn_scale), ptr(bn_shift),
-                                          ptr(residual), int(bool(relu)), ptr(out), ptr(out_bf16), st))
+                                          ptr(residual), ptr(residual_bf16), int(bool(relu)), ptr(out), ptr(out_bf16),
+                                          st))
         else:
             raise ValueError(f"unknown precision {precision!r}")
         if timing is not None:

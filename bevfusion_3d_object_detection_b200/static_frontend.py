@@ -147,9 +147,12 @@ class StaticFrontEnd:
         for op in self.ops:
             chans[op["level_out"]] = max(chans.get(op["level_out"], 0), op["conv"].out_channels)
         self.slots = {}
+        last_lvl = self.ops[-1]["level_out"]
         for lvl, c in chans.items():
             cap = self.levels[lvl].cap
-            self.slots[lvl] = [dict(f32=torch.empty((cap, c), dtype=torch.float32, device=dev),
+            need32 = (not bf16) or lvl == last_lvl or any(
+                op["conv"].need_f32 for op in self.ops if op["level_out"] == lvl)
+            self.slots[lvl] = [dict(f32=torch.empty((cap, c), dtype=torch.float32, device=dev) if need32 else None,
                                     bf16=torch.empty((cap, c), dtype=torch.bfloat16, device=dev) if bf16 else None)
                                for _ in range(3)]
         cap0 = self.levels[0].cap
@@ -210,7 +213,7 @@ class StaticFrontEnd:
         # 3. the 21 convolutions
         for lv in self.levels:
             lv.subm_fresh.clear()
-        cur = dict(f32=self.in_f32, bf16=self.in_bf16)
+        cur = dict(f32=self.in_f32, bf16=self.in_bf16, f32_valid=self.in_f32 is not None)
         cur_slot = -1
         block_in = None
         for op in self.ops:
@@ -239,15 +242,25 @@ class StaticFrontEnd:
             # output slot: any of the level's three that is neither the input nor the pending block input
             slots = self.slots[op["level_out"]]
             out = next(s for s in slots if s is not cur and s is not block_in)
-            residual = block_in["f32"] if op["residual"] == "block_in" else None
+            residual = None
+            if op["residual"] == "block_in" and block_in.get("f32_valid", False):
+                residual = block_in["f32"]
             w = conv._packed_weight(self.precision)
             if self.precision == "bf16":
                 cin_pad = int(L.bevf_spconv_tc_cin_pad(conv.in_channels))
+                # same choices as the module path: fp32 copy only where a layer asks for it, skip connection from the
+                # fp32 copy if the block input has one, else from its bf16 operand copy
+                residual_bf16 = None
+                if op["residual"] == "block_in" and residual is None:
+                    residual_bf16 = block_in["bf16"]
+                out_f32 = out["f32"] if conv.need_f32 else None
+                out["f32_valid"] = out_f32 is not None
                 check(L.bevf_spconv_gemm_bf16(ptr(cur["bf16"]), lin.cap, ptr(w), ptr(pair), lout.ld, lout.hint,
                                               ptr(lout.n_dev), kv, cin_pad, conv.out_channels, ptr(conv.bias),
-                                              ptr(op["scale"]), ptr(op["shift"]), ptr(residual), int(op["relu"]),
-                                              ptr(out["f32"]), ptr(out["bf16"]), st))
+                                              ptr(op["scale"]), ptr(op["shift"]), ptr(residual), ptr(residual_bf16),
+                                              int(op["relu"]), ptr(out_f32), ptr(out["bf16"]), st))
             else:
+                out["f32_valid"] = True
                 check(L.bevf_spconv_gemm_f32(ptr(cur["f32"]), ptr(w), ptr(pair), lout.ld, lout.hint, ptr(lout.n_dev), kv,
                                              conv.in_channels, conv.out_channels, ptr(conv.bias), ptr(op["scale"]),
                                              ptr(op["shift"]), ptr(residual), int(op["relu"]), ptr(out["f32"]), st))

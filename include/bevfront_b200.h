@@ -286,7 +286,8 @@ int bevf_spconv_gemm_f32(const float *feats, const float *weight_kio, const int 
  * bf16 tensor-core path (TMA tile::gather4 -> tcgen05.mma, fp32 accumulation in TMEM): features bf16 [n_in, cin_pad] (cin_pad =
  * bevf_spconv_tc_cin_pad(cin) in {16,32,64,128}, zero padded: bevf_spconv_cast_bf16), weights packed per tap into
  * the UMMA K-major core-matrix image (bevf_spconv_pack_weight_bf16, kv*cout*cin_pad bf16).  Cout in
- * {16,32,64,128}.  Writes fp32 (out_f32) and/or bf16 (out_bf16, feeds the next layer without a cast pass).
+ * {16,32,64,128}.  Writes fp32 (out_f32) and/or bf16 (out_bf16, feeds the next layer without a cast pass).  The
+ * residual is read as fp32 [n_out, cout] (residual) or as the bf16 copy a previous layer wrote (residual_bf16).
  */
 int bevf_spconv_tc_cin_pad(int cin);
 int bevf_spconv_tc_supported(int cin, int cout);
@@ -296,8 +297,8 @@ int bevf_spconv_pack_weight_bf16(const float *weight_okc, void *weight_packed, i
                                  void *stream);
 int bevf_spconv_gemm_bf16(const void *feats_bf16, int n_in, const void *weight_packed, const int *pair_fwd, int ld, int n_out,
                           const int *n_out_dev, int kv, int cin_pad, int cout, const float *bias,
-                          const float *bn_scale, const float *bn_shift, const float *residual, int relu,
-                          float *out_f32, void *out_bf16, void *stream);
+                          const float *bn_scale, const float *bn_shift, const float *residual,
+                          const void *residual_bf16, int relu, float *out_f32, void *out_bf16, void *stream);
 
 #ifdef __cplusplus
 }
