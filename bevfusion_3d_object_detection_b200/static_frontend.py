@@ -191,8 +191,9 @@ class StaticFrontEnd:
         self.depth.copy_(depth, non_blocking=True)
         self.ctx.copy_(ctx, non_blocking=True)
 
-    def _enqueue(self):
-        """The whole frame as a fixed sequence of launches on the current stream (capturable)."""
+    def _enqueue(self, gemm_events=None):
+        """The whole frame as a fixed sequence of launches on the current stream (capturable).  `gemm_events`: list
+        that receives a (start, end) CUDA event pair around every gather-GEMM launch (profiling, eager only)."""
         L, dev = lib(), self.dev
         st = cur_stream(dev)
         vs, rg = f32_array(self.voxel_size), f32_array(self.pc_range)
@@ -246,6 +247,9 @@ class StaticFrontEnd:
             if op["residual"] == "block_in" and block_in.get("f32_valid", False):
                 residual = block_in["f32"]
             w = conv._packed_weight(self.precision)
+            if gemm_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             if self.precision == "bf16":
                 cin_pad = int(L.bevf_spconv_tc_cin_pad(conv.in_channels))
                 # same choices as the module path: fp32 copy only where a layer asks for it, skip connection from the
@@ -264,6 +268,9 @@ class StaticFrontEnd:
                 check(L.bevf_spconv_gemm_f32(ptr(cur["f32"]), ptr(w), ptr(pair), lout.ld, lout.hint, ptr(lout.n_dev), kv,
                                              conv.in_channels, conv.out_channels, ptr(conv.bias), ptr(op["scale"]),
                                              ptr(op["shift"]), ptr(residual), int(op["relu"]), ptr(out["f32"]), st))
+            if gemm_events is not None:
+                ev[1].record()
+                gemm_events.append(ev)
             if op["residual"] == "block_in":
                 block_in = None
             cur = out
@@ -315,6 +322,28 @@ class StaticFrontEnd:
     def replay(self):
         self.graph.replay()
         return self.lidar_bev, self.cam_bev
+
+    @torch.no_grad()
+    def profile(self, reps=5):
+        """Device time of every gather-GEMM launch (best of `reps` eager runs) and its useful flops
+        (2 * valid rulebook pairs * Cin * Cout).  -> list of dict(cin, cout, subm, ms, flops, rows)."""
+        best = None
+        with torch.cuda.device(self.dev):
+            for _ in range(reps):
+                evs = []
+                self._enqueue(gemm_events=evs)
+                torch.cuda.synchronize(self.dev)
+                ms = [a.elapsed_time(b) for a, b in evs]
+                best = ms if best is None else [min(x, y) for x, y in zip(best, ms)]
+        counts = self.counts()
+        out = []
+        for op, ms in zip(self.ops, best):
+            conv = op["conv"]
+            n = counts[op["level_out"]]
+            pairs = int((op["pair"][:, :n] >= 0).sum().item())
+            out.append(dict(cin=conv.in_channels, cout=conv.out_channels, subm=bool(conv.subm), ms=ms, rows=n,
+                            flops=2.0 * pairs * conv.in_channels * conv.out_channels))
+        return out
 
     def counts(self):
         """Active sites per level (one host sync; diagnostics only)."""
