@@ -179,7 +179,7 @@ def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from bevfusion_3d_object_detection_b200 import _lib, frontend, spconv, synthetic
+    from bevfusion_3d_object_detection_b200 import _lib, frontend, parallel, spconv, synthetic
     from bevfusion_3d_object_detection_b200.spconv import functional as Fsp
 
     if not torch.cuda.is_available():
@@ -254,10 +254,7 @@ def run_b200(args, rank, world, local_rank):
             launches = L.bevf_launch_count() - n0
             if plan is not None and fn is step_dev:
                 launches = launches_per_frame * steps   # graph replays do not pass through the launch counter
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        _, ms, _ = parallel.job_throughput(steps, ms, device=dev)   # max over ranks
         return ms, launches
 
     sampler = ClockSampler(local_rank)
