@@ -36,16 +36,24 @@ struct ConvGeom {
 __device__ __forceinline__ long long lin_cell(const Grid &g, int b, int x, int y, int z) {
   return (((long long)b * g.x + x) * g.y + y) * g.z + z;
 }
+// IT = unsigned (grids below 2^31 cells: the hot kernels then run on 32-bit integer math) or long long
+template <typename IT>
+__device__ __forceinline__ IT lin_cell_t(const Grid &g, int b, int x, int y, int z) {
+  return (((IT)b * (IT)g.x + (IT)x) * (IT)g.y + (IT)y) * (IT)g.z + (IT)z;
+}
 
+template <typename IT>
 __device__ __forceinline__ int index_lookup(const IndexView &ix, int b, int x, int y, int z) {
   if ((unsigned)x >= (unsigned)ix.g.x || (unsigned)y >= (unsigned)ix.g.y || (unsigned)z >= (unsigned)ix.g.z) return -1;
-  const long long cell = lin_cell(ix.g, b, x, y, z);
+  const IT cell = lin_cell_t<IT>(ix.g, b, x, y, z);
   const unsigned bits = __ldg(ix.bitmap + (cell >> 5));
   const unsigned bit = (unsigned)(cell & 31);
   if (!((bits >> bit) & 1u)) return -1;
   const int rank = __ldg(ix.word_prefix + (cell >> 5)) + __popc(bits & ((1u << bit) - 1u));
   return ix.perm ? __ldg(ix.perm + rank) : rank;
 }
+
+constexpr int kRbBlocks = bevf::kNumSMs * 16;  // grid-stride kernels: the grid never grows with the buffer capacity
 
 // every kernel below takes the row count either from the host (n) or, when n_dev != NULL, from device memory
 // (min(*n_dev, n): n is then the capacity the grid was sized for) so a whole frame can run without a host sync
@@ -85,93 +93,111 @@ __global__ void fill_perm_kernel(const int *__restrict__ indices, int n, const i
   perm[rank] = i;
 }
 
-// SubM: out sites == in sites; kernel centred; one thread per (site, tap-x/y column), 3..k[2] z-taps share the
-// bitmap word most of the time.
+// SubM: out sites == in sites; kernel centred; one work item per (site, tap-x/y column), the k[2] z-taps of a
+// column share the bitmap word most of the time.  Grid-stride over n * kx * ky items (n possibly from the device).
+template <typename IT>
 __global__ void __launch_bounds__(256)
     subm_rulebook_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, IndexView ix,
                          ConvGeom cg, int ld, int *__restrict__ pair_fwd) {
-  const int kxy = cg.k[0] * cg.k[1];
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)n * kxy) return;
-  const int j = (int)(t % n);  // consecutive threads -> consecutive sites: coalesced pair_fwd stores
-  if (n_dev && j >= *n_dev) return;
-  const int col = (int)(t / n);
-  const int kx = col / cg.k[1], ky = col % cg.k[1];
-  const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + j);
-  const int x = c.y + (kx - cg.k[0] / 2) * cg.d[0];
-  const int y = c.z + (ky - cg.k[1] / 2) * cg.d[1];
-  for (int kz = 0; kz < cg.k[2]; ++kz) {
-    const int z = c.w + (kz - cg.k[2] / 2) * cg.d[2];
-    const int tap = col * cg.k[2] + kz;
-    pair_fwd[(size_t)tap * ld + j] = index_lookup(ix, c.x, x, y, z);
-  }
-}
-
-// strided conv, pass 1: every input marks the output sites it reaches
-__global__ void __launch_bounds__(256)
-    strided_mark_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom cg, Grid og,
-                        unsigned *__restrict__ out_bitmap) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
-  if (i >= n) return;
-  const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
-  for (int kx = 0; kx < cg.k[0]; ++kx) {
-    int ox = c.y + cg.p[0] - kx * cg.d[0];
-    if (ox < 0 || ox % cg.s[0]) continue;
-    ox /= cg.s[0];
-    if (ox >= og.x) continue;
-    for (int ky = 0; ky < cg.k[1]; ++ky) {
-      int oy = c.z + cg.p[1] - ky * cg.d[1];
-      if (oy < 0 || oy % cg.s[1]) continue;
-      oy /= cg.s[1];
-      if (oy >= og.y) continue;
-      for (int kz = 0; kz < cg.k[2]; ++kz) {
-        int oz = c.w + cg.p[2] - kz * cg.d[2];
-        if (oz < 0 || oz % cg.s[2]) continue;
-        oz /= cg.s[2];
-        if (oz >= og.z) continue;
-        long long cell = lin_cell(og, c.x, ox, oy, oz);
-        unsigned m = 1u << (unsigned)(cell & 31);
-        if (!(out_bitmap[cell >> 5] & m)) atomicOr(out_bitmap + (cell >> 5), m);
-      }
+  const unsigned kxy = (unsigned)(cg.k[0] * cg.k[1]);
+  const unsigned total = (unsigned)n * kxy;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned col = t / (unsigned)n;
+    const int j = (int)(t - col * (unsigned)n);  // consecutive threads -> consecutive sites: coalesced stores
+    const int kx = (int)(col / (unsigned)cg.k[1]), ky = (int)(col % (unsigned)cg.k[1]);
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + j);
+    const int x = c.y + (kx - cg.k[0] / 2) * cg.d[0];
+    const int y = c.z + (ky - cg.k[1] / 2) * cg.d[1];
+    for (int kz = 0; kz < cg.k[2]; ++kz) {
+      const int z = c.w + (kz - cg.k[2] / 2) * cg.d[2];
+      const int tap = (int)col * cg.k[2] + kz;
+      pair_fwd[(size_t)tap * ld + j] = index_lookup<IT>(ix, c.x, x, y, z);
     }
   }
 }
 
-struct EmitSites {
-  Grid og;
-  int *out_indices;
-  int cap;
-  __device__ void operator()(int rank, unsigned long long key) const {
-    if (rank >= cap) return;
-    int4 o;
-    o.w = (int)(key % (unsigned)og.z); key /= (unsigned)og.z;
-    o.z = (int)(key % (unsigned)og.y); key /= (unsigned)og.y;
-    o.y = (int)(key % (unsigned)og.x); key /= (unsigned)og.x;
-    o.x = (int)key;
-    reinterpret_cast<int4 *>(out_indices)[rank] = o;
+// strided conv, pass 1: every input marks the output sites it reaches; one work item per (input, kx, ky)
+template <typename IT>
+__global__ void __launch_bounds__(256)
+    strided_mark_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom cg, Grid og,
+                        unsigned *__restrict__ out_bitmap) {
+  if (n_dev) n = min(n, *n_dev);
+  const unsigned kxy = (unsigned)(cg.k[0] * cg.k[1]);
+  const unsigned total = (unsigned)n * kxy;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned col = t / (unsigned)n;
+    const int i = (int)(t - col * (unsigned)n);
+    const int kx = (int)(col / (unsigned)cg.k[1]), ky = (int)(col % (unsigned)cg.k[1]);
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+    int ox = c.y + cg.p[0] - kx * cg.d[0];
+    if (ox < 0 || ox % cg.s[0]) continue;
+    ox /= cg.s[0];
+    if (ox >= og.x) continue;
+    int oy = c.z + cg.p[1] - ky * cg.d[1];
+    if (oy < 0 || oy % cg.s[1]) continue;
+    oy /= cg.s[1];
+    if (oy >= og.y) continue;
+    for (int kz = 0; kz < cg.k[2]; ++kz) {
+      int oz = c.w + cg.p[2] - kz * cg.d[2];
+      if (oz < 0 || oz % cg.s[2]) continue;
+      oz /= cg.s[2];
+      if (oz >= og.z) continue;
+      const IT cell = lin_cell_t<IT>(og, c.x, ox, oy, oz);
+      const unsigned m = 1u << (unsigned)(cell & 31);
+      if (!(out_bitmap[cell >> 5] & m)) atomicOr(out_bitmap + (cell >> 5), m);
+    }
   }
-};
+}
+
+// strided conv, pass 1b: output sites in ascending cell order from the scanned bitmap (one work item per word)
+template <typename IT>
+__global__ void __launch_bounds__(256)
+    emit_sites_kernel(const unsigned *__restrict__ bitmap, const int *__restrict__ word_prefix, long long nwords,
+                      Grid og, int *__restrict__ out_indices, int cap) {
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+       w += (long long)gridDim.x * blockDim.x) {
+    unsigned bits = __ldg(bitmap + w);
+    if (!bits) continue;
+    int rank = __ldg(word_prefix + w);
+    const IT base = (IT)w << 5;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (rank < cap) {
+        IT key = base + (IT)b;
+        int4 o;
+        o.w = (int)(key % (IT)og.z); key /= (IT)og.z;
+        o.z = (int)(key % (IT)og.y); key /= (IT)og.y;
+        o.y = (int)(key % (IT)og.x); key /= (IT)og.x;
+        o.x = (int)key;
+        reinterpret_cast<int4 *>(out_indices)[rank] = o;
+      }
+      rank += 1;
+    }
+  }
+}
 
 // strided conv, pass 2: for every output site and tap, look the input up
+template <typename IT>
 __global__ void __launch_bounds__(256)
     strided_rulebook_kernel(const int *__restrict__ out_indices, const int *__restrict__ n_out_dev, int n_out_host,
                             IndexView ix, ConvGeom cg, int ld, int *__restrict__ pair_fwd) {
   const int n_out = n_out_dev ? min(*n_out_dev, ld) : n_out_host;
-  const int kxy = cg.k[0] * cg.k[1];
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)ld * kxy) return;
-  const int j = (int)(t % ld);
-  if (j >= n_out) return;
-  const int col = (int)(t / ld);
-  const int kx = col / cg.k[1], ky = col % cg.k[1];
-  const int4 o = __ldg(reinterpret_cast<const int4 *>(out_indices) + j);
-  const int x = o.y * cg.s[0] - cg.p[0] + kx * cg.d[0];
-  const int y = o.z * cg.s[1] - cg.p[1] + ky * cg.d[1];
-  for (int kz = 0; kz < cg.k[2]; ++kz) {
-    const int z = o.w * cg.s[2] - cg.p[2] + kz * cg.d[2];
-    const int tap = col * cg.k[2] + kz;
-    pair_fwd[(size_t)tap * ld + j] = index_lookup(ix, o.x, x, y, z);
+  const unsigned kxy = (unsigned)(cg.k[0] * cg.k[1]);
+  const unsigned total = (unsigned)n_out * kxy;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned col = t / (unsigned)n_out;
+    const int j = (int)(t - col * (unsigned)n_out);
+    const int kx = (int)(col / (unsigned)cg.k[1]), ky = (int)(col % (unsigned)cg.k[1]);
+    const int4 o = __ldg(reinterpret_cast<const int4 *>(out_indices) + j);
+    const int x = o.y * cg.s[0] - cg.p[0] + kx * cg.d[0];
+    const int y = o.z * cg.s[1] - cg.p[1] + ky * cg.d[1];
+    for (int kz = 0; kz < cg.k[2]; ++kz) {
+      const int z = o.w * cg.s[2] - cg.p[2] + kz * cg.d[2];
+      const int tap = (int)col * cg.k[2] + kz;
+      pair_fwd[(size_t)tap * ld + j] = index_lookup<IT>(ix, o.x, x, y, z);
+    }
   }
 }
 
@@ -340,9 +366,13 @@ BEVF_API int bevf_spconv_subm_rulebook(const int *indices, int n, const int *n_d
   IndexView ix{m.bitmap, m.word_prefix, perm, Grid{batch, shape[0], shape[1], shape[2]}};
   ConvGeom cg;
   fill_geom(cg, ksize, nullptr, nullptr, dilation);
-  long long threads = (long long)n * ksize[0] * ksize[1];
-  subm_rulebook_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, n_dev, ix, cg, ld,
-                                                                                        pair_fwd);
+  const long long threads = (long long)n * ksize[0] * ksize[1];
+  BEVF_CHECK_ARG(threads < (1ll << 32), "rulebook with %lld (site, tap column) items is not supported", threads);
+  const int blocks = (int)(bevf::ceil_div(threads, 256) < kRbBlocks ? bevf::ceil_div(threads, 256) : kRbBlocks);
+  if (nwords < (1ll << 26))
+    subm_rulebook_kernel<unsigned><<<blocks, 256, 0, (cudaStream_t)stream>>>(indices, n, n_dev, ix, cg, ld, pair_fwd);
+  else
+    subm_rulebook_kernel<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(indices, n, n_dev, ix, cg, ld, pair_fwd);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;
 }
@@ -372,12 +402,21 @@ BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, const in
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
   if (n_in > 0) {
-    strided_mark_kernel<<<bevf::ceil_div(n_in, 256), 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+    const long long items = (long long)n_in * ksize[0] * ksize[1];
+    BEVF_CHECK_ARG(items < (1ll << 32), "%lld (site, tap column) items are not supported", items);
+    const int blocks = (int)(bevf::ceil_div(items, 256) < kRbBlocks ? bevf::ceil_div(items, 256) : kRbBlocks);
+    if (nwords < (1ll << 26)) strided_mark_kernel<unsigned><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+    else strided_mark_kernel<long long><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
     BEVF_CHECK_LAUNCH();
   }
-  rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitSites{og, out_indices, cap},
-                        st);
+  rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitNothing{}, st);
   if (rc) return rc;
+  {
+    const int blocks = (int)(bevf::ceil_div(nwords, 256) < kRbBlocks ? bevf::ceil_div(nwords, 256) : kRbBlocks);
+    if (nwords < (1ll << 26)) emit_sites_kernel<unsigned><<<blocks, 256, 0, st>>>(m.bitmap, m.word_prefix, nwords, og, out_indices, cap);
+    else emit_sites_kernel<long long><<<blocks, 256, 0, st>>>(m.bitmap, m.word_prefix, nwords, og, out_indices, cap);
+    BEVF_CHECK_LAUNCH();
+  }
   if (n_out_dev)
     BEVF_CHECK_CUDA(cudaMemcpyAsync(n_out_dev, m.scalars, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return BEVF_OK;
@@ -400,9 +439,16 @@ BEVF_API int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, con
   IndexView ix{m.bitmap, m.word_prefix, in_perm, Grid{batch, in_shape[0], in_shape[1], in_shape[2]}};
   ConvGeom cg;
   fill_geom(cg, ksize, stride, padding, dilation);
-  long long threads = (long long)ld * ksize[0] * ksize[1];
-  strided_rulebook_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(out_indices, n_out_dev,
-                                                                                           n_out, ix, cg, ld, pair_fwd);
+  const long long threads = (long long)(n_out_dev ? ld : n_out) * ksize[0] * ksize[1];
+  BEVF_CHECK_ARG(threads < (1ll << 32), "rulebook with %lld (site, tap column) items is not supported", threads);
+  if (threads == 0) return BEVF_OK;
+  const int blocks = (int)(bevf::ceil_div(threads, 256) < kRbBlocks ? bevf::ceil_div(threads, 256) : kRbBlocks);
+  if (nwords < (1ll << 26))
+    strided_rulebook_kernel<unsigned><<<blocks, 256, 0, (cudaStream_t)stream>>>(out_indices, n_out_dev, n_out, ix, cg, ld,
+                                                                                pair_fwd);
+  else
+    strided_rulebook_kernel<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(out_indices, n_out_dev, n_out, ix, cg, ld,
+                                                                                 pair_fwd);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;
 }
