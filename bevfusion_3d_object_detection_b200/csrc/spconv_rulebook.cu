@@ -215,16 +215,29 @@ __global__ void __launch_bounds__(256)
 }
 
 // BEVFusionSparseEncoder tail (sparse_encoder.py:147-151): dense() [N,C,X,Y,Z] -> permute(0,1,4,2,3) ->
-// view(N, C*Z, X, Y), fused: bev[b, ch*Z + z, x, y]
+// view(N, C*Z, X, Y), fused: bev[b, ch*Z + z, x, y].  A CTA takes 32 consecutive sites: their feature rows are read
+// coalesced into shared memory, then each warp writes one channel at a time for the 32 sites -- with sites in
+// ascending (x, y, z) order the 32 destinations of a channel are a few runs of consecutive y.
 __global__ void __launch_bounds__(256)
     to_bev_kernel(const float *__restrict__ feats, const int *__restrict__ indices, int n,
                   const int *__restrict__ n_dev, int c, Grid g, float *__restrict__ bev) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float tile[];  // [32][c + 1]
+  __shared__ int4 site[32];
   if (n_dev) n = min(n, *n_dev);
-  if (t >= (long long)n * c) return;
-  const int i = (int)(t / c), ch = (int)(t % c);
-  const int4 q = __ldg(reinterpret_cast<const int4 *>(indices) + i);
-  bev[((((size_t)q.x * c + ch) * g.z + q.w) * g.x + q.y) * g.y + q.z] = feats[t];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {
+    const int cnt = min(32, n - i0);
+    if (threadIdx.x < cnt) site[threadIdx.x] = __ldg(reinterpret_cast<const int4 *>(indices) + i0 + threadIdx.x);
+    for (int e = threadIdx.x; e < cnt * c; e += blockDim.x) tile[(e / c) * (c + 1) + e % c] = feats[(size_t)i0 * c + e];
+    __syncthreads();
+    if (lane < cnt) {
+      const int4 q = site[lane];
+      const size_t base = ((size_t)q.x * c * g.z + q.w) * g.x * g.y + (size_t)q.y * g.y + q.z;
+      const size_t cstride = (size_t)g.z * g.x * g.y;
+      for (int ch = warp; ch < c; ch += 8) bev[base + ch * cstride] = tile[lane * (c + 1) + ch];
+    }
+    __syncthreads();
+  }
 }
 
 // rows re-ordered by perm (rank -> row): out_indices[r] = indices[perm[r]], features copied as fp32 and/or as bf16
@@ -462,7 +475,11 @@ BEVF_API int bevf_sparse_to_dense(const float *feats, const int *indices, int n,
   if (n == 0) return BEVF_OK;
   Grid g{batch, shape[0], shape[1], shape[2]};
   long long threads = (long long)n * c;
-  if (bev_layout) to_bev_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, n_dev, c, g, dense);
+  if (bev_layout) {
+    const int blocks = bevf::ceil_div(n, 32) < kRbBlocks ? bevf::ceil_div(n, 32) : kRbBlocks;
+    BEVF_CHECK_ARG((size_t)32 * (c + 1) * sizeof(float) <= 48 * 1024, "too many channels for the BEV scatter (%d)", c);
+    to_bev_kernel<<<blocks, 256, (size_t)32 * (c + 1) * sizeof(float), st>>>(feats, indices, n, n_dev, c, g, dense);
+  }
   else to_dense_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, n_dev, c, g, dense);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;

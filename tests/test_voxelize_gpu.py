@@ -190,3 +190,35 @@ def test_dynamic_scatter_module_and_edges(oracle_mod):
     assert vf.shape[0] == 0 and vc.shape[0] == 0
     with pytest.raises(RuntimeError, match="reduce type"):
         ops.dynamic_scatter(torch.ones(10, 4, device="cuda"), torch.zeros(10, 3, dtype=torch.int32, device="cuda"), "min")
+
+
+def test_mmcv_style_zyx_spelling(oracle_mod):
+    """mmdet3d's data-preprocessor spelling (coords zyx, count through a tensor) == the project spelling flipped;
+    the reference's known answer (test_voxel_generator.py:7-20) is stated in zyx."""
+    from bevfusion_3d_object_detection_b200.ops.voxel import mmcv_style
+
+    np.random.seed(0)
+    points = np.random.uniform(0, 4, (20, 3)).astype(np.float32)
+    v, c, n = mmcv_style.voxelization(torch.from_numpy(points).cuda(), [5, 5, 1], [0, 0, 0, 20, 40, 4], 5, 20000, True)
+    np.testing.assert_array_equal(c.cpu().numpy(), [[2, 0, 0], [3, 0, 0], [0, 0, 0], [1, 0, 0]])
+    np.testing.assert_array_equal(n.cpu().numpy(), [5, 5, 5, 3])
+    pts = synthetic.lidar_sweeps(n_sweeps=1, seed=9)
+    layer = mmcv_style.VoxelizationByGridShape(synthetic.NUSCENES_RANGE, 10, voxel_size=synthetic.NUSCENES_VOXEL,
+                                               max_voxels=(120000, 160000)).eval()
+    assert layer.grid_shape == [1440, 1440, 40]
+    v, c, n = layer(torch.from_numpy(pts).cuda())
+    ov, oc, on = oracle_mod.hard_voxelize(pts, synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, 10, 160000)
+    np.testing.assert_array_equal(c.cpu().numpy(), oc[:, ::-1])
+    np.testing.assert_array_equal(n.cpu().numpy(), on)
+    np.testing.assert_array_equal(v.cpu().numpy(), ov)
+    # dynamic form: CPU contract of mmcv (a failed point is (-1, -1, -1)), zyx
+    dyn = mmcv_style.voxelization(torch.from_numpy(pts).cuda(), synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, -1, -1)
+    want = oracle_mod.dynamic_voxelize(pts, synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, gpu_partial=False)
+    np.testing.assert_array_equal(dyn.cpu().numpy(), want[:, ::-1])
+    # scatter with return_map
+    feats = torch.from_numpy(pts).cuda()
+    vf, vc, pmap = mmcv_style.dynamic_scatter_3d(feats, dyn.contiguous(), "mean", True)
+    assert pmap.shape[0] == pts.shape[0] and vf.shape[0] == vc.shape[0] == int(pmap.max()) + 1
+    scat = mmcv_style.DynamicScatter3D(synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, True)
+    vf2, vc2 = scat(feats, dyn.contiguous())
+    assert torch.equal(vf2, vf) and torch.equal(vc2, vc)
