@@ -221,4 +221,5 @@ def test_mmcv_style_zyx_spelling(oracle_mod):
     assert pmap.shape[0] == pts.shape[0] and vf.shape[0] == vc.shape[0] == int(pmap.max()) + 1
     scat = mmcv_style.DynamicScatter3D(synthetic.NUSCENES_VOXEL, synthetic.NUSCENES_RANGE, True)
     vf2, vc2 = scat(feats, dyn.contiguous())
-    assert torch.equal(vf2, vf) and torch.equal(vc2, vc)
+    # float atomics: the sum order (and so the last bits of a mean) differs run to run
+    assert torch.equal(vc2, vc) and torch.allclose(vf2, vf, rtol=1e-5, atol=1e-5)
