@@ -83,6 +83,10 @@ class StaticFrontEnd:
         self.ctx = None
         self.graph = None
         self.cam_bev = None
+        # side streams: rulebooks and the camera branch run beside the GEMM chain (also inside the captured graph)
+        self.overlap = True
+        self.s_rule = torch.cuda.Stream(dev)
+        self.s_cam = torch.cuda.Stream(dev)
 
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
@@ -198,6 +202,15 @@ class StaticFrontEnd:
         st = cur_stream(dev)
         vs, rg = f32_array(self.voxel_size), f32_array(self.pc_range)
         lv0 = self.levels[0]
+        # 0. the camera branch shares nothing with the LiDAR branch: its own stream, joined at the end
+        if self.overlap:
+            fork0 = torch.cuda.Event()
+            fork0.record(torch.cuda.current_stream(dev))
+            self.s_cam.wait_event(fork0)
+            with torch.cuda.stream(self.s_cam):
+                self._enqueue_camera(cur_stream(dev))
+                cam_done = torch.cuda.Event()
+                cam_done.record(self.s_cam)
         # 1. voxelize + mean + batch pad, appended sample after sample at the device row offset
         lv0.n_dev.zero_()
         for k in range(self.batch):
@@ -211,33 +224,58 @@ class StaticFrontEnd:
         check(L.bevf_spconv_permute_rows(ptr(self.vox_feats), ptr(self.vox_coords), ptr(self.perm0), lv0.cap,
                                          ptr(lv0.n_dev), self.c_in, self.cin_pad, ptr(self.in_f32), ptr(self.in_bf16),
                                          ptr(lv0.indices), st))
-        # 3. the 21 convolutions
-        for lv in self.levels:
-            lv.subm_fresh.clear()
+        # 3. every rulebook on a side stream: they depend on coordinates only, so the index / site / rulebook kernels of
+        #    the later levels overlap the gather-GEMMs of the earlier ones (which leave most SM threads idle).  The
+        #    camera branch is independent of the LiDAR branch altogether and gets its own stream.
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        if self.overlap:
+            self.s_rule.wait_event(fork)
+        rule_stream = self.s_rule if self.overlap else main
+        with torch.cuda.stream(rule_stream):
+            st_r = cur_stream(dev)
+            for lv in self.levels:
+                lv.subm_fresh.clear()
+            for op in self.ops:
+                conv = op["conv"]
+                lin, lout = self.levels[op["level_in"]], self.levels[op["level_out"]]
+                ks, st_, pd, dl = (i32_array(conv.kernel_size), i32_array(conv.stride), i32_array(conv.padding),
+                                   i32_array(conv.dilation))
+                pair = op["pair"]
+                op["ready"] = None
+                if conv.subm:
+                    if op["subm_key"] not in lin.subm_fresh:
+                        check(L.bevf_spconv_subm_rulebook(ptr(lin.indices), lin.cap, ptr(lin.n_dev), self.batch,
+                                                          lin.shape_c, ks, dl, ptr(lin.index_mem),
+                                                          ctypes.c_size_t(lin.index_bytes), None, ptr(pair), lin.ld,
+                                                          st_r))
+                        lin.subm_fresh.add(op["subm_key"])
+                        if self.overlap:
+                            op["ready"] = torch.cuda.Event()
+                            op["ready"].record(rule_stream)
+                else:
+                    check(L.bevf_spconv_strided_sites(ptr(lin.indices), lin.cap, ptr(lin.n_dev), self.batch,
+                                                      lin.shape_c, ks, st_, pd, dl, ptr(lout.index_mem),
+                                                      ctypes.c_size_t(lout.index_bytes), ptr(lout.indices), lout.cap,
+                                                      ptr(lout.n_dev), st_r))
+                    check(L.bevf_spconv_strided_rulebook(ptr(lout.indices), lout.cap, ptr(lout.n_dev), self.batch,
+                                                         lin.shape_c, ks, st_, pd, dl, ptr(lin.index_mem),
+                                                         ctypes.c_size_t(lin.index_bytes), None, ptr(pair), lout.ld,
+                                                         st_r))
+                    if self.overlap:
+                        op["ready"] = torch.cuda.Event()
+                        op["ready"].record(rule_stream)
+        # 4. the 21 gather-GEMMs on the main stream, each after its rulebook
         cur = dict(f32=self.in_f32, bf16=self.in_bf16, f32_valid=self.in_f32 is not None)
-        cur_slot = -1
         block_in = None
         for op in self.ops:
             conv = op["conv"]
             lin, lout = self.levels[op["level_in"]], self.levels[op["level_out"]]
-            ks, st_, pd, dl = (i32_array(conv.kernel_size), i32_array(conv.stride), i32_array(conv.padding),
-                               i32_array(conv.dilation))
             kv = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
             pair = op["pair"]
-            if conv.subm:
-                if op["subm_key"] not in lin.subm_fresh:
-                    check(L.bevf_spconv_subm_rulebook(ptr(lin.indices), lin.cap, ptr(lin.n_dev), self.batch,
-                                                      lin.shape_c, ks, dl, ptr(lin.index_mem),
-                                                      ctypes.c_size_t(lin.index_bytes), None, ptr(pair), lin.ld, st))
-                    lin.subm_fresh.add(op["subm_key"])
-            else:
-                check(L.bevf_spconv_strided_sites(ptr(lin.indices), lin.cap, ptr(lin.n_dev), self.batch, lin.shape_c,
-                                                  ks, st_, pd, dl, ptr(lout.index_mem),
-                                                  ctypes.c_size_t(lout.index_bytes), ptr(lout.indices), lout.cap,
-                                                  ptr(lout.n_dev), st))
-                check(L.bevf_spconv_strided_rulebook(ptr(lout.indices), lout.cap, ptr(lout.n_dev), self.batch,
-                                                     lin.shape_c, ks, st_, pd, dl, ptr(lin.index_mem),
-                                                     ctypes.c_size_t(lin.index_bytes), None, ptr(pair), lout.ld, st))
+            if op["ready"] is not None:
+                main.wait_event(op["ready"])
             if op["block_start"]:
                 block_in = cur
             # output slot: any of the level's three that is neither the input nor the pending block input
@@ -274,12 +312,20 @@ class StaticFrontEnd:
             if op["residual"] == "block_in":
                 block_in = None
             cur = out
-        # 4. dense()+permute+view of the last level
+        # 5. dense()+permute+view of the last level
         last = self.levels[self.ops[-1]["level_out"]]
         c_last = self.ops[-1]["conv"].out_channels
         check(L.bevf_sparse_to_dense(ptr(cur["f32"]), ptr(last.indices), last.cap, ptr(last.n_dev), c_last, self.batch,
                                      last.shape_c, ptr(self.lidar_bev), 1, st))
-        # 5. camera branch: context to channels-last, ray-major partial sums, cell-major gather
+        # 6. camera branch (already in flight on its own stream when overlapping)
+        if self.overlap:
+            main.wait_event(cam_done)
+        else:
+            self._enqueue_camera(st)
+
+    def _enqueue_camera(self, st):
+        """context to channels-last, ray-major partial sums, cell-major gather (csrc/bev_pool.cu)."""
+        L = lib()
         t = self.tables
         bn, c, fh, fw = self.ctx.shape
         d = self.depth.shape[1]

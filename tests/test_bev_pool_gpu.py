@@ -118,10 +118,14 @@ def _view_case(batch, n_cams, feature_size, image_size, D_bound, C, xb, seed):
     return vt, geom, depth, ctx
 
 
-@pytest.mark.parametrize("case", ["small_b2", "config_A"])
+@pytest.mark.parametrize("case", ["small_b2", "config_A", "config_C_custom", "stress_D236_b2"])
 def test_fused_forward_matches_reference_chain(oracle_mod, case):
     if case == "small_b2":
         vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 1)
+    elif case == "config_C_custom":  # BASELINE configs[3]: 5 cams, 384x704 image, 48x88 features
+        vt, geom, depth, ctx = _view_case(1, 5, (48, 88), (384, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 6)
+    elif case == "stress_D236_b2":   # BASELINE configs[4]: 236 depth bins (dbound step 0.25), 2 frames per GPU
+        vt, geom, depth, ctx = _view_case(2, 6, (32, 88), (256, 704), [1.0, 60.0, 0.25], 80, [-54.0, 54.0, 0.3], 7)
     else:  # BASELINE configs[0]/[1]: 6 cams x 118 x 32 x 88 x 80 ch -> 360 x 360
         vt, geom, depth, ctx = _view_case(1, 6, (32, 88), (256, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 0)
     B, N, D, fH, fW, _ = geom.shape
