@@ -381,6 +381,13 @@ def run_b200(args, rank, world, local_rank):
         roof = dict(kernel="voxelize_mean (5 kernels)", bound="hbm", achieved=stages["voxelize_mean"]["gbs"],
                     peak=pk["hbm"], unit="GB/s", frac=stages["voxelize_mean"]["frac"], traffic=None)
     roof["peak_source"] = pk["src"]
+    tpath = os.path.join(ROOT, "profiles", "r1h_traffic.json")
+    if roof["bound"] == "tensor" and os.path.exists(tpath):
+        tr = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of the 21 launches (ncu --set full)
+        roof["traffic"] = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / n_gemm
+        roof["traffic_note"] = "DRAM bytes per launch, mean over the frame's %d launches (%s)" % (n_gemm, tr["source"])
+    roof["launches_per_frame"] = n_gemm
+    roof["avg_launch_ms"] = gemm_ms / max(n_gemm, 1)
 
     if rank != 0:
         if world > 1:
