@@ -136,6 +136,9 @@ def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, preci
             assert residual_bf16.shape[1] == cout
         else:
             residual = residual.contiguous().float()
+    if n_out == 0:  # empty level: nothing to launch (zero-sized tensors have no device pointer to pass)
+        return out, (torch.empty((0, cout), dtype=torch.bfloat16, device=dev)
+                     if (precision == "bf16" and want_bf16) else None)
     timing = GEMM_TIMING
     if timing is not None:
         pairs = int((pair_fwd[:, :n_out] >= 0).sum().item())

@@ -62,3 +62,29 @@ def test_static_plan_batch2():
     plan.load_inputs(pts, depth, ctx)
     gl, gc = plan.run()
     assert gl.shape == (2, 256, 180, 180) and torch.equal(gl, wl) and torch.equal(gc, wc)
+
+
+def test_empty_and_tiny_frames():
+    """A frame with no point inside the range, then one with a single voxel: every level empty / one site; both
+    paths return the same (zero / single-column) maps without tripping on zero-sized launches."""
+    torch.manual_seed(2)
+    model = frontend.BEVFrontEnd(precision="bf16").cuda().eval()
+    rig = {k: torch.from_numpy(v).cuda() for k, v in synthetic.camera_rig(6, (256, 704), 1).items()}
+    tables = model.set_calibration(rig)
+    depth, ctx = synthetic.camera_features(6, 118, 80, (32, 88), batch=1, seed=3)
+    depth, ctx = torch.from_numpy(depth).cuda(), torch.from_numpy(ctx).cuda()
+    plan = StaticFrontEnd(model, tables, "cuda", batch=1, max_points=5000)
+    far = torch.full((100, 5), 500.0, device="cuda")                       # all out of range
+    one = torch.tensor([[1.0, 2.0, -1.0, 7.0, 0.0]] * 3, device="cuda")     # three points, one voxel
+    for pts, n_sites in ((far, 0), (one, 1), (far, 0)):
+        with torch.no_grad():
+            wl, wc = model([pts], depth, ctx, tables)
+        plan.load_inputs([pts], depth, ctx)
+        gl, gc = plan.run()
+        torch.cuda.synchronize()
+        assert plan.counts()[0] == n_sites
+        assert torch.equal(gl, wl) and torch.equal(gc, wc)
+        if n_sites == 0:
+            assert float(gl.abs().max()) == 0.0
+        else:
+            assert float(gl.abs().max()) > 0.0
