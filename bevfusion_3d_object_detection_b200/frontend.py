@@ -75,15 +75,20 @@ class HostPipeline:
         from .static_frontend import StaticFrontEnd
 
         self.device = torch.device(device)
-        self.compute = torch.cuda.current_stream(self.device)
+        # one compute stream per plan: consecutive frames overlap on the GPU (the head of frame i+1 -- voxelizer,
+        # index build -- and its small kernels fill the SMs the tail of frame i leaves idle)
+        self.computes = [torch.cuda.Stream(self.device) for _ in range(depth)]
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self.depth = depth
         self.plans = [StaticFrontEnd(model, tables, device, batch=batch, max_points=max_points) for _ in range(depth)]
         if example is not None:  # (points list, depth, ctx): representative frame for warm-up + capture
-            for p in self.plans:
-                p.load_inputs(*example)
-                p.capture()
+            for p, c in zip(self.plans, self.computes):
+                c.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(c):
+                    p.load_inputs(*example)
+                    p.capture()
+                torch.cuda.current_stream(self.device).wait_stream(c)
         self.host = [None] * depth           # (lidar_host, cam_host) pinned
         self.e_comp = [None] * depth         # plan's graph finished (its inputs may be overwritten)
         self.e_done = [None] * depth         # plan's outputs copied out (its outputs may be overwritten)
@@ -95,18 +100,20 @@ class HostPipeline:
         slot = self.n % self.depth
         self.n += 1
         plan = self.plans[slot]
+        compute = self.computes[slot]
         with torch.cuda.stream(self.s_in):
             if self.e_comp[slot] is not None:
                 self.s_in.wait_event(self.e_comp[slot])
             plan.load_inputs(points, depth, ctx)
             e_in = torch.cuda.Event()
             e_in.record(self.s_in)
-        self.compute.wait_event(e_in)
-        if self.e_done[slot] is not None:
-            self.compute.wait_event(self.e_done[slot])
-        lidar, cam = plan.replay() if plan.graph is not None else plan.run()
-        self.e_comp[slot] = torch.cuda.Event()
-        self.e_comp[slot].record(self.compute)
+        with torch.cuda.stream(compute):
+            compute.wait_event(e_in)
+            if self.e_done[slot] is not None:
+                compute.wait_event(self.e_done[slot])
+            lidar, cam = plan.replay() if plan.graph is not None else plan.run()
+            self.e_comp[slot] = torch.cuda.Event()
+            self.e_comp[slot].record(compute)
         if self.host[slot] is None:
             self.host[slot] = (torch.empty(lidar.shape, dtype=lidar.dtype).pin_memory(),
                                torch.empty(cam.shape, dtype=cam.dtype).pin_memory())
@@ -123,6 +130,29 @@ class HostPipeline:
         self.e_done[slot].synchronize()
         return self.host[slot]
 
+    def submit_device(self, points, depth, ctx):
+        """Same rotation for inputs that already live on the device (no host copies): -> (slot, lidar, cam); the
+        returned maps are the plan's own buffers, valid until the slot comes round again."""
+        slot = self.n % self.depth
+        self.n += 1
+        plan, compute = self.plans[slot], self.computes[slot]
+        caller = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(compute):
+            compute.wait_stream(caller)          # the caller's writes to the inputs are ordered before the copy
+            plan.load_inputs(points, depth, ctx)
+            lidar, cam = plan.replay() if plan.graph is not None else plan.run()
+            self.e_comp[slot] = torch.cuda.Event()
+            self.e_comp[slot].record(compute)
+        return slot, lidar, cam
+
+    def join(self, stream=None):
+        """Make `stream` (default: the current one) wait for everything submitted so far."""
+        stream = stream or torch.cuda.current_stream(self.device)
+        for c in self.computes:
+            stream.wait_stream(c)
+        stream.wait_stream(self.s_out)
+
     def drain(self):
         self.s_out.synchronize()
-        self.compute.synchronize()
+        for c in self.computes:
+            c.synchronize()
