@@ -14,7 +14,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -185,7 +184,7 @@ def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from bevfusion_3d_object_detection_b200 import _lib, frontend, parallel, spconv, synthetic
+    from bevfusion_3d_object_detection_b200 import _lib, frontend, parallel, synthetic
     from bevfusion_3d_object_detection_b200.spconv import functional as Fsp
 
     if not torch.cuda.is_available():

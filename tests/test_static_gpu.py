@@ -1,6 +1,5 @@
 """The sync-free execution plan (StaticFrontEnd, eager and as a CUDA graph) gives bit-identical BEV maps to the
 module path (BEVFrontEnd.forward), frame after frame with changing point counts."""
-import numpy as np
 import pytest
 import torch
 
