@@ -227,7 +227,7 @@ def run_b200(args, rank, world, local_rank):
         plan.load_inputs([f["points"]], f["depth"], f["ctx"])   # device -> static input buffers (20 MB)
         return plan.replay()                                    # the whole frame: one CUDA graph
 
-    pipe = frontend.HostPipeline(model, tables, dev, depth=2, batch=1, max_points=max_pts,
+    pipe = frontend.HostPipeline(model, tables, dev, depth=max(2, args.inflight), batch=1, max_points=max_pts,
                                  example=([ex["points"]], ex["depth"], ex["ctx"]) if args.mode == "graph" else None)
     out_host = {}
 
@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("BEVFRONT_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
-    ap.add_argument("--inflight", type=int, default=2, help="frames in flight per GPU (graph mode): 1 or 2")
+    ap.add_argument("--inflight", type=int, default=3, help="frames in flight per GPU (graph mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
