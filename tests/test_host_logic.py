@@ -138,3 +138,68 @@ def test_run_tables_describe_the_same_pooling(oracle_mod):
     st, lg = oracle_mod.intervals_from_ranks(ranks.numpy())
     ref = oracle_mod.bev_pool_fused(depth, ctx, src, gf.numpy().astype(np.int32), st, lg, B, nz, nx, ny)
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_sparse_conv_module_surface_and_checkpoint_shim():
+    """spconv-2.x constructor / parameter layout, the registry route the reference builds its layers through
+    (sparse_block.py:201-217), and the checkpoint weight-layout shim of write_spconv2.py:43-104."""
+    import pytest
+    from bevfusion_3d_object_detection_b200 import registry, spconv
+
+    registry.register_all()
+    conv = registry.build_conv_layer(dict(type="SubMConv3d", indice_key="subm1"), 5, 16, 3, padding=1, bias=False)
+    assert isinstance(conv, spconv.SubMConv3d) and conv.subm and conv.indice_key == "subm1"
+    assert tuple(conv.weight.shape) == (16, 3, 3, 3, 5) and conv.bias is None        # (Cout, kD, kH, kW, Cin)
+    down = registry.build_conv_layer(dict(type="SparseConv3d", indice_key="spconv3"), 64, 128, 3, stride=2,
+                                     padding=(1, 1, 0), bias=False)
+    assert not down.subm and down.stride == [2, 2, 2] and down.padding == [1, 1, 0]
+    with pytest.raises(KeyError):
+        registry.build_conv_layer(dict(type="NoSuchConv"), 1, 1, 3)
+    for bad in (dict(groups=2), dict(transposed=True), dict(inverse=True)):
+        with pytest.raises(NotImplementedError):
+            spconv.SparseConvolution(3, 4, 4, **bad)
+    with pytest.raises(NotImplementedError):
+        spconv.SparseConvolution(2, 4, 4)
+    # a checkpoint saved by spconv 1.x / mmcv stores (kD, kH, kW, Cin, Cout): no version in the metadata -> permuted
+    w_old = torch.randn(3, 3, 3, 5, 16)
+    sd = {"weight": w_old.clone()}
+    conv.load_state_dict(sd)
+    assert torch.equal(conv.weight.data, w_old.permute(4, 0, 1, 2, 3))
+    # a version-2 checkpoint (what this module itself saves) loads unchanged
+    sd2 = conv.state_dict()
+    assert sd2._metadata[""]["version"] == 2
+    conv2 = spconv.SubMConv3d(5, 16, 3, padding=1, bias=False)
+    conv2.load_state_dict(sd2)
+    assert torch.equal(conv2.weight.data, conv.weight.data)
+    # wrong shape is reported, not silently accepted
+    with pytest.raises(RuntimeError):
+        conv.load_state_dict({"weight": torch.randn(3, 3, 3, 4, 16)})
+
+
+def test_encoder_layout_and_state_dict_keys():
+    """BEVFusionSparseEncoder with the nuScenes config: 21 sparse convs, the reference's module names (so its
+    checkpoints load by key), strided convs carry the reference's indice keys, only conv_out keeps fp32 output."""
+    from bevfusion_3d_object_detection_b200 import spconv
+    from bevfusion_3d_object_detection_b200.sparse_encoder import NUSCENES_ENCODER_CFG, BEVFusionSparseEncoder
+
+    enc = BEVFusionSparseEncoder(**NUSCENES_ENCODER_CFG)
+    convs = [(n, m) for n, m in enc.named_modules() if isinstance(m, spconv.SparseConvolution)]
+    assert len(convs) == 21
+    keys = set(enc.state_dict().keys())
+    for k in ("conv_input.0.weight", "conv_input.1.running_mean", "encoder_layers.encoder_layer1.0.conv1.weight",
+              "encoder_layers.encoder_layer1.0.bn1.weight", "encoder_layers.encoder_layer1.1.conv2.weight",
+              "encoder_layers.encoder_layer1.2.0.weight", "encoder_layers.encoder_layer3.2.0.weight",
+              "encoder_layers.encoder_layer4.1.bn2.running_var", "conv_out.0.weight", "conv_out.1.bias"):
+        assert k in keys, k
+    assert not any(k.endswith(".bias") and ".0." in k and "conv" in k.split(".")[-2] for k in keys)
+    by_name = dict(convs)
+    assert by_name["conv_input.0"].indice_key == "subm1" and by_name["conv_input.0"].in_channels == 5
+    assert [by_name[f"encoder_layers.encoder_layer{i}.2.0"].indice_key for i in (1, 2, 3)] == ["spconv1", "spconv2",
+                                                                                                "spconv3"]
+    assert by_name["encoder_layers.encoder_layer3.2.0"].padding == [1, 1, 0]
+    out = by_name["conv_out.0"]
+    assert out.kernel_size == [1, 1, 3] and out.stride == [1, 1, 2] and out.indice_key == "spconv_down2"
+    assert out.need_f32 and sum(m.need_f32 for _, m in convs) == 1
+    assert tuple(by_name["encoder_layers.encoder_layer4.0.conv1"].weight.shape) == (128, 3, 3, 3, 128)
+    n_params = sum(p.numel() for p in enc.parameters())
+    assert 2.5e6 < n_params < 3.0e6   # SURVEY 8e: ~2.7 M parameters
