@@ -97,3 +97,27 @@ def camera_features(n_cams=6, D=118, C=80, feature_size=(32, 88), batch=1, seed=
     depth = (e / e.sum(1, keepdims=True)).astype(np.float32)
     ctx = rng.standard_normal((batch * n_cams, C, fh, fw)).astype(np.float32)
     return depth, ctx
+
+
+def camera_matrices(rig, lidar_yaw=0.0, lidar_scale=1.0, lidar_trans=(0.0, 0.0, 0.0)):
+    """The 4x4 form of a `camera_rig` as BaseDepthTransform.forward takes it (depth_lss.py:333-362):
+    lidar2image [B,N,4,4] = K @ inv(camera2lidar), img_aug_matrix [B,N,4,4], lidar_aug_matrix [B,4,4]
+    (rotation about z by `lidar_yaw`, scale, translation) -- float32."""
+    B, N = rig["camera2lidar_trans"].shape[:2]
+    l2i = np.zeros((B, N, 4, 4), np.float64)
+    aug = np.zeros((B, N, 4, 4), np.float64)
+    for b in range(B):
+        for n in range(N):
+            c2l = np.eye(4)
+            c2l[:3, :3] = rig["camera2lidar_rots"][b, n]
+            c2l[:3, 3] = rig["camera2lidar_trans"][b, n]
+            K = np.eye(4)
+            K[:3, :3] = np.linalg.inv(rig["intrins_inverse"][b, n].astype(np.float64))
+            l2i[b, n] = K @ np.linalg.inv(c2l)
+            aug[b, n] = np.eye(4)
+            aug[b, n, :3, :3] = np.linalg.inv(rig["post_rots_inverse"][b, n].astype(np.float64))
+            aug[b, n, :3, 3] = rig["post_trans"][b, n]
+    laug = np.tile(np.eye(4), (B, 1, 1))
+    laug[:, :3, :3] = _rot_z(lidar_yaw) * lidar_scale
+    laug[:, :3, 3] = np.asarray(lidar_trans, np.float64)
+    return l2i.astype(np.float32), aug.astype(np.float32), laug.astype(np.float32)

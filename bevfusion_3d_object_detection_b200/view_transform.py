@@ -11,7 +11,7 @@ from typing import Tuple
 import torch
 from torch import nn
 
-from .ops import BevPoolTables, bev_pool, bev_pool_fused
+from .ops import BevPoolTables, bev_pool, bev_pool_fused, depth_histogram, lidar_depth_image
 
 
 def gen_dx_bx(xbound, ybound, zbound):
@@ -118,3 +118,19 @@ class BaseViewTransform(nn.Module):
         get_cam_feats' outer product (depth_lss.py:723-725) followed by bev_pool(), without the 638 MB
         frustum tensor or any of its copies."""
         return bev_pool_fused(depth, ctx, self._tables if tables is None else tables)
+
+
+class BaseDepthTransform(BaseViewTransform):
+    """The data-path half of depth_lss.py:333-520 (BaseDepthTransform.forward) and :632-661 (get_cam_feats'
+    histogram): LiDAR points -> sparse depth image -> per-cell depth-bin counts / distribution.  The conv stacks
+    that consume them stay with the caller."""
+
+    def lidar_depth(self, points, lidar2image, img_aug_matrix, lidar_aug_matrix, lidar_aug_matrix_inverse=None):
+        """-> depth [B, N, 1, H, W] (depth_lss.py:366-420)"""
+        return lidar_depth_image(points, lidar2image, img_aug_matrix, lidar_aug_matrix, self.image_size,
+                                 lidar_aug_matrix_inverse)
+
+    def depth_distribution(self, depth):
+        """depth [B, N, 1, H, W] -> (gt_depth_distr, counts_3d), each [B, N, fH, fW, D] (depth_lss.py:632-661)"""
+        counts, distr = depth_histogram(depth, self.feature_size, self.dbound, self.D)
+        return distr, counts

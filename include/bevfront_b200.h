@@ -203,6 +203,31 @@ int bevf_nchw_to_nhwc(const float *src, float *dst, int n, int c, int hw, void *
 int bevf_nhwc_to_nchw(const float *src, float *dst, int n, int c, int hw, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ *
+ * Upstream of bev_pool: LiDAR depth image and its per-feature-cell histogram
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * BaseDepthTransform.forward's per-sample loop (projects/BEVFusion/bevfusion/depth_lss.py:372-420) for ONE sample:
+ * every point is taken back through the LiDAR augmentation (p - lidar_aug_trans, then lidar_aug_inv_rot [3,3]),
+ * into each camera (lidar2image [n_cams,4,4]), divided by its clamped depth, through the image augmentation
+ * (img_aug [n_cams,4,4]); points landing inside the H x W image write their camera-frame z into
+ * depth [n_cams, H, W] (zero elsewhere; fully written).  Where several points hit one pixel the LARGEST point index
+ * wins (a sequential scatter_; the reference's CUDA scatter_ keeps an arbitrary one).  owner_ws: n_cams*H*W int32.
+ * All matrices row-major fp32 on the device.
+ */
+int bevf_lidar_depth_image(const float *points, int num_points, int num_features, const float *lidar_aug_trans,
+                           const float *lidar_aug_inv_rot, const float *lidar2image, const float *img_aug, int n_cams,
+                           int h, int w, float *depth, int *owner_ws, void *stream);
+/*
+ * The histogram block of DepthLSSTransform.get_cam_feats (depth_lss.py:632-661): counts [BN, fH, fW, D] = number of
+ * pixels of each (h/fH) x (w/fW) cell whose depth falls in bin trunc((clamp(d, d0, d1 - dd/2) + dd/2 - d0) / dd), bin 0
+ * (no depth) cleared; distr = counts / (sum + 1e-8).  (A pixel in bin D, d >= d1 - dd/2, is dropped: in the reference it
+ * lands in the next cell's bin 0, which is cleared as well.)
+ */
+int bevf_depth_histogram(const float *depth, int bn, int h, int w, int fh, int fw, int d, float d0, float d1, float dd,
+                         float *counts, float *distr, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ *
  * Sparse 3-D convolution (SubMConv3d / SparseConv3d of spconv >= 2.3, the third-party dependency the
  * reference builds its encoder from: mmdet3d/models/layers/spconv/overwrite_spconv/write_spconv2.py:21-38,
  * mmdet3d/models/layers/sparse_block.py:201-217, projects/BEVFusion/bevfusion/sparse_encoder.py:131-147;

@@ -193,6 +193,30 @@ def bev_pool_fused(depth, ctx, src, geom4, starts, lengths, B, nz, nx, ny):
     return out.reshape(B, C * nz, nx, ny)
 
 
+def lidar_depth_image(points, laug_trans, laug_inv_rot, lidar2image, img_aug, H, W):
+    """depth_lss.py:372-420 for one sample -> depth [n_cams, H, W]"""
+    points = _f32(points)
+    l2i, ia = _f32(lidar2image), _f32(img_aug)
+    n_cams = l2i.shape[0]
+    depth = np.zeros((n_cams, H, W), np.float32)
+    lib().oracle_lidar_depth_image(_p(points, _f32p), points.shape[0], points.shape[1], _p(_f32(laug_trans), _f32p),
+                                   _p(_f32(laug_inv_rot), _f32p), _p(l2i, _f32p), _p(ia, _f32p), n_cams, H, W,
+                                   _p(depth, _f32p))
+    return depth
+
+
+def depth_histogram(depth, fH, fW, D, dbound):
+    """depth_lss.py:632-661: depth [bn, H, W] -> (counts, distr) [bn, fH, fW, D]"""
+    depth = _f32(depth)
+    bn, H, W = depth.shape
+    counts = np.zeros((bn, fH, fW, D), np.float32)
+    distr = np.zeros_like(counts)
+    f = ctypes.c_float
+    lib().oracle_depth_histogram(_p(depth, _f32p), bn, H, W, fH, fW, D, f(dbound[0]), f(dbound[1]), f(dbound[2]),
+                                 _p(counts, _f32p), _p(distr, _f32p))
+    return counts, distr
+
+
 def _i3(v):
     if isinstance(v, int):
         v = (v, v, v)

@@ -560,3 +560,73 @@ ORACLE_API void oracle_bn_relu(float *x, const float *residual, int n, int c, co
       x[(size_t)i * c + ch] = v;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------ *
+ * LiDAR depth image + depth histogram (upstream of bev_pool)
+ *   pinned against fixtures generated by running the reference's BaseDepthTransform.forward /
+ *   DepthLSSTransform.get_cam_feats on CPU (tests/golden/make_golden.py depth_prep()).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Roundings as the reference's CPU run performs them (checked against tests/golden/depth_prep.npz): the batched
+ * per-camera products accumulate with fma in k order, the single [3,3] x [3,N] product rounds every term.  (The file is
+ * compiled with -ffp-contract=off, so a * b + c below is two roundings.) */
+static float o_dot3(float a0, float a1, float a2, float x, float y, float z) {
+  return fmaf(a2, z, fmaf(a1, y, a0 * x));
+}
+static float o_dot3_rounded(float a0, float a1, float a2, float x, float y, float z) {
+  const float s = a0 * x + a1 * y;
+  return s + a2 * z;
+}
+
+/* projects/BEVFusion/bevfusion/depth_lss.py:372-420, one sample.  depth [n_cams, H, W] fully written.
+ * Duplicates: the sequential scatter_ (:417) leaves the LAST (camera, point) pair in nonzero order, i.e. the largest
+ * point index of each pixel. */
+ORACLE_API void oracle_lidar_depth_image(const float *points, int n, int c, const float *laug_t,
+                                         const float *laug_inv_r, const float *l2i_all, const float *iaug_all,
+                                         int n_cams, int H, int W, float *depth) {
+  memset(depth, 0, sizeof(float) * (size_t)n_cams * H * W);
+  for (int cam = 0; cam < n_cams; ++cam) {
+    const float *l2i = l2i_all + cam * 16, *ia = iaug_all + cam * 16;
+    for (int i = 0; i < n; ++i) {
+      const float *p = points + (size_t)i * c;
+      const float x0 = p[0] - laug_t[0], y0 = p[1] - laug_t[1], z0 = p[2] - laug_t[2];          /* :379 */
+      const float x1 = o_dot3_rounded(laug_inv_r[0], laug_inv_r[1], laug_inv_r[2], x0, y0, z0);          /* :380 */
+      const float y1 = o_dot3_rounded(laug_inv_r[3], laug_inv_r[4], laug_inv_r[5], x0, y0, z0);
+      const float z1 = o_dot3_rounded(laug_inv_r[6], laug_inv_r[7], laug_inv_r[8], x0, y0, z0);
+      float x2 = o_dot3(l2i[0], l2i[1], l2i[2], x1, y1, z1) + l2i[3];                            /* :383-384 */
+      float y2 = o_dot3(l2i[4], l2i[5], l2i[6], x1, y1, z1) + l2i[7];
+      const float z2 = o_dot3(l2i[8], l2i[9], l2i[10], x1, y1, z1) + l2i[11];
+      const float zc = fminf(fmaxf(z2, 1e-5f), 1e5f);                                            /* :387 (dist aliases it) */
+      x2 = x2 / zc;                                                                              /* :388 */
+      y2 = y2 / zc;
+      const float x3 = o_dot3(ia[0], ia[1], ia[2], x2, y2, zc) + ia[3];                          /* :391-392 */
+      const float y3 = o_dot3(ia[4], ia[5], ia[6], x2, y2, zc) + ia[7];
+      if (!(y3 < (float)H && y3 >= 0.f && x3 < (float)W && x3 >= 0.f)) continue;                 /* :399-404 */
+      depth[((size_t)cam * H + (int)y3) * W + (int)x3] = zc;                                     /* :411-417 */
+    }
+  }
+}
+
+/* depth_lss.py:632-661.  counts / distr: [bn, fH, fW, D] */
+ORACLE_API void oracle_depth_histogram(const float *depth, int bn, int H, int W, int fH, int fW, int D, float d0,
+                                       float d1, float dd, float *counts, float *distr) {
+  const size_t total = (size_t)bn * fH * fW * D;
+  memset(counts, 0, sizeof(float) * total);
+  const float dmax = (float)((double)d1 - 0.5 * (double)dd), half = (float)(0.5 * (double)dd);
+  const int ph = H / fH, pw = W / fW;
+  for (int cam = 0; cam < bn; ++cam)
+    for (int r = 0; r < H; ++r)
+      for (int q = 0; q < W; ++q) {
+        const float d = depth[((size_t)cam * H + r) * W + q];
+        const float t = (fminf(fmaxf(d, d0), dmax) + half - d0) / dd;
+        const long long flat = ((long long)cam * fH * fW + (long long)(r / ph) * fW + q / pw) * D + (long long)t;
+        if (flat >= 0 && (size_t)flat < total) counts[flat] += 1.f; /* bin D spills into the next cell's bin 0 */
+      }
+  for (size_t cell = 0; cell < (size_t)bn * fH * fW; ++cell) {
+    float *h = counts + cell * D;
+    h[0] = 0.f;
+    float s = 0.f;
+    for (int b = 0; b < D; ++b) s += h[b];
+    for (int b = 0; b < D; ++b) distr[cell * D + b] = h[b] / (s + 1e-8f);
+  }
+}

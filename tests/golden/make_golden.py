@@ -9,6 +9,8 @@ oracle/ref_loader.py, and its C++ CPU ops are compiled into oracle/_ref by oracl
                         dynamic_voxelize_cpu ("asis" on a cubic grid, "fixed" = lookup-table shape fix)
   view_geometry.npz     projects/BEVFusion/bevfusion/depth_lss.py BaseViewTransform.get_geometry + bev_pool_aux
   quick_cumsum.npz      projects/BEVFusion/bevfusion/ops/bev_pool/bev_pool.py QuickCumsum (pure torch)
+  depth_prep.npz        depth_lss.py BaseDepthTransform.forward (LiDAR depth image, :372-420) and
+                        DepthLSSTransform.get_cam_feats (counts_3d / gt_depth_distr, :632-661), run on CPU
 """
 import os
 import sys
@@ -100,12 +102,57 @@ def quick_cumsum():
                         pooled=pooled.numpy(), pooled_geom=pooled_geom.numpy())
 
 
+def depth_prep():
+    dl = ref_loader.depth_lss()
+    H, W, fH, fW = 64, 176, 8, 22
+    dbound = [1.0, 30.0, 0.5]
+    torch.manual_seed(0)
+    vt = dl.DepthLSSTransform(8, 6, (H, W), (fH, fW), [-12.0, 12.0, 0.75], [-12.0, 12.0, 0.75], [-10.0, 10.0, 20.0],
+                              dbound)
+    vt.eval()
+    B, N = 2, 3
+    rig = synthetic.camera_rig(n_cams=N, image_size=(H, W), batch=B, src_size=(900, 1600), resize=0.12)
+    l2i, iaug, laug = synthetic.camera_matrices(rig, lidar_yaw=0.1, lidar_scale=1.05, lidar_trans=(0.5, -0.2, 0.1))
+    laug[1] = np.eye(4, dtype=np.float32)  # second sample: no LiDAR augmentation
+    points = [synthetic.lidar_sweeps(n_sweeps=1, beams=32, azimuth=720, seed=1 + b)[:, :3].copy() for b in range(B)]
+    # nothing on this path multiplies by lidar_aug's rotation, only by its inverse: augment the points so they
+    # project sensibly
+    for b in range(B):
+        points[b][:, :3] = points[b][:, :3] @ laug[b, :3, :3].T + laug[b, :3, 3]
+
+    class Captured(Exception):
+        pass
+
+    def grab(img, depth):
+        raise Captured(depth)
+
+    img = torch.randn(B, N, 8, fH, fW)
+    eye = torch.eye(4).repeat(B, N, 1, 1)
+    vt.get_cam_feats = grab
+    try:
+        with torch.no_grad():
+            # the reference subtracts lidar_aug's translation from the caller's points in place (:379): pass copies
+            vt.forward(img, [torch.from_numpy(p.copy()) for p in points], torch.from_numpy(l2i), eye.clone(),
+                       eye.clone(), torch.from_numpy(iaug), torch.from_numpy(laug), None, None, None, None, None)
+        raise AssertionError("get_cam_feats was not reached")
+    except Captured as e:
+        depth = e.args[0]
+    del vt.get_cam_feats
+    with torch.no_grad():
+        _, _, gt_depth_distr, counts_3d = vt.get_cam_feats(img, depth.clone())
+    np.savez_compressed(os.path.join(OUT, "depth_prep.npz"), points0=points[0], points1=points[1], lidar2image=l2i,
+                        img_aug_matrix=iaug, lidar_aug_matrix=laug, depth=depth.numpy(),
+                        counts_3d=counts_3d.numpy(), gt_depth_distr=gt_depth_distr.numpy(), image_size=[H, W],
+                        feature_size=[fH, fW], dbound=dbound, D=vt.D)
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     voxel_numba()
     voxel_ref_cpp()
     view_geometry()
     quick_cumsum()
+    depth_prep()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
