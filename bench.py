@@ -425,8 +425,8 @@ def run_b200(args, rank, world, local_rank):
     try:
         from bevfusion_3d_object_detection_b200 import ops as _ops
 
-        rig = synthetic.camera_rig(n_cams=N_CAMS, image_size=IMAGE)
-        l2i, iaug, laug = (torch.from_numpy(a).to(dev) for a in synthetic.camera_matrices(rig))
+        rig_np = synthetic.camera_rig(n_cams=N_CAMS, image_size=IMAGE)
+        l2i, iaug, laug = (torch.from_numpy(a).to(dev) for a in synthetic.camera_matrices(rig_np))
         linv = torch.inverse(laug)
         pts0 = dev_frames[0]["points"]
         dimg = torch.empty((1, N_CAMS, 1) + tuple(IMAGE), device=dev)
@@ -441,6 +441,31 @@ def run_b200(args, rank, world, local_rank):
             timing="CUDA graph of %d calls each; not part of the timed frame step" % RING)
     except Exception as exc:
         print(f"[bench] depth-prep timing unavailable: {exc}", file=sys.stderr)
+    # ---- upstream "next" row: the pooling tables from the frustum geometry, device-side vs the
+    #      reference's bev_pool_aux formulation (argsort + masked gathers); per calibration, so outside the frame step
+    try:
+        import time as _time
+
+        vt = model.view_transform
+        geom = vt.get_geometry(**rig)
+
+        def wall_ms(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t0 = _time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (_time.perf_counter() - t0) * 1e3 / reps
+
+        ms_tb_dev = wall_ms(lambda: vt.build_tables(geom, device_build=True), 10)
+        ms_tb_aux = wall_ms(lambda: vt.build_tables(geom, device_build=False), 3)
+        vt._tables = tables
+        stages["pool_tables"] = dict(device_build_ms=ms_tb_dev, bev_pool_aux_route_ms=ms_tb_aux,
+                                     points=int(geom.numel() // 3),
+                                     timing="host wall clock per build, including its size read-back")
+    except Exception as exc:
+        print(f"[bench] table-build timing unavailable: {exc}", file=sys.stderr)
     # the dominant kernel family of the step
     if gemm_ms >= max(ms_vox, ms_pool):
         roof = dict(kernel="spconv_tc_kernel (21 launches, aggregate)", bound="tensor",

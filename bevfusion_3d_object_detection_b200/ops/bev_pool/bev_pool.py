@@ -154,6 +154,61 @@ class BevPoolTables:
         if frustum_shape is not None and nk > 0:
             self._build_runs(src.long(), cell.long(), frustum_shape)
 
+    _workspaces = {}
+
+    @classmethod
+    def from_geometry(cls, geom, B, bx, dx, nx):
+        """Device-side build (csrc/bev_tables.cu): geom [B, N, D, fH, fW, 3] CUDA fp32 -> the same tables as
+        `BevPoolTables(*bev_pool_aux(geom), ...)`, bit for bit, in ~10 kernels and one 12-byte read-back.
+        bx / dx / nx: the view transform's grid (first-cell centre, cell size, (nx, ny, nz) counts)."""
+        if not geom.is_cuda:
+            raise RuntimeError("BevPoolTables.from_geometry: CUDA tensors only (use the bev_pool_aux form on CPU)")
+        import ctypes
+
+        from ..._lib import f32_array
+
+        Bg, N, D, fH, fW, three = geom.shape
+        assert three == 3 and Bg == B
+        geom = geom.contiguous().float()
+        dev = geom.device
+        nxi, nyi, nzi = (int(v) for v in nx)
+        nprime = Bg * N * D * fH * fW
+        cells = B * nzi * nxi * nyi
+        cap_int = min(nprime, cells)
+        L = lib()
+        L.bevf_bev_pool_tables_workspace_bytes.restype = ctypes.c_size_t
+        ws_bytes = int(L.bevf_bev_pool_tables_workspace_bytes(ctypes.c_longlong(nprime), B, nzi, nxi, nyi))
+        key = (dev, ws_bytes)
+        ws = cls._workspaces.get(key)
+        if ws is None:
+            ws = cls._workspaces[key] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        n_tiles = int(L.bevf_bev_pool_num_tiles(B, nzi, nxi, nyi))
+
+        def i32(n):
+            return torch.empty(n, dtype=torch.int32, device=dev)
+
+        t = cls.__new__(cls)
+        cop, src, run_p0, run_len, run_ids = i32(nprime), i32(nprime), i32(nprime), i32(nprime), i32(nprime)
+        istarts, icell, crs = i32(cap_int + 1), i32(cap_int), i32(cap_int + 1)
+        tile_starts, col_starts, counts = i32(n_tiles + 1), i32(Bg * N * fW + 1), i32(4)
+        with torch.cuda.device(dev):
+            check(L.bevf_bev_pool_build_tables(
+                ptr(geom), Bg * N, D, fH, fW, B, f32_array([float(v) for v in bx]), f32_array([float(v) for v in dx]),
+                nxi, nyi, nzi, ptr(cop), ptr(src), ptr(istarts), ptr(icell), ptr(tile_starts), ptr(run_p0),
+                ptr(run_len), ptr(col_starts), ptr(run_ids), ptr(crs), ptr(counts), ptr(ws),
+                ctypes.c_size_t(ws_bytes), cur_stream(dev)))
+        nk, n_int, n_runs = (int(v) for v in counts[:3].tolist())   # the one host round trip
+        t.nk, t.n_intervals, t.n_runs = nk, n_int, n_runs
+        t.src = src[:nk]
+        t.interval_cell = icell[:n_int]
+        t.interval_starts = istarts[:n_int + 1]
+        t.cell_of_point = cop
+        t.B, t.nz, t.nx, t.ny = int(B), nzi, nxi, nyi
+        t.run_p0, t.run_len, t.cell_run_ids = run_p0[:n_runs], run_len[:n_runs], run_ids[:n_runs]
+        t.col_run_starts, t.cell_run_starts, t.tile_starts = col_starts, crs[:n_int + 1], tile_starts
+        t.use_runs = nk > 0 and n_runs * 4 <= nk
+        return t
+
     def _build_runs(self, p, cell, frustum_shape):
         _, D, fH, fW = [int(v) for v in frustum_shape]
         plane = fH * fW

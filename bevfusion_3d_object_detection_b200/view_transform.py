@@ -104,10 +104,17 @@ class BaseViewTransform(nn.Module):
         return torch.cat(x.unbind(dim=2), 1)  # collapse Z
 
     # ---- fused north-star path ----------------------------------------------------------------------
-    def build_tables(self, geom, B=None):
-        """Per-calibration tables for `pool_fused` from a geometry tensor [B,N,D,fH,fW,3]."""
-        geom_feats, kept, ranks, indices = self.bev_pool_aux(geom)
+    def build_tables(self, geom, B=None, device_build=None):
+        """Per-calibration tables for `pool_fused` from a geometry tensor [B,N,D,fH,fW,3].  CUDA geometry goes
+        through the device-side builder (csrc/bev_tables.cu: no argsort, no host round trips but the final sizes);
+        `device_build=False` (and CPU geometry) takes the reference's bev_pool_aux route."""
         B = geom.shape[0] if B is None else B
+        if device_build is None:
+            device_build = geom.is_cuda
+        if device_build:
+            self._tables = BevPoolTables.from_geometry(geom, B, self.bx.tolist(), self.dx.tolist(), self.nx.tolist())
+            return self._tables
+        geom_feats, kept, ranks, indices = self.bev_pool_aux(geom)
         Bg, N, D, fH, fW, _ = geom.shape
         self._tables = BevPoolTables(geom_feats, kept, ranks, indices, B, int(self.nx[2]), int(self.nx[0]),
                                      int(self.nx[1]), frustum_shape=(Bg * N, D, fH, fW))

@@ -202,6 +202,28 @@ int bevf_bev_pool_fused_backward(const float *out_grad_nhwc, const float *depth,
 int bevf_nchw_to_nhwc(const float *src, float *dst, int n, int c, int hw, void *stream);
 int bevf_nhwc_to_nchw(const float *src, float *dst, int n, int c, int hw, void *stream);
 
+/*
+ * Device-side construction of every pooling table from the frustum geometry: what
+ * BaseViewTransform.bev_pool_aux (projects/BEVFusion/bevfusion/depth_lss.py:118-176) plus the interval construction
+ * of bev_pool() (ops/bev_pool/bev_pool.py:158-166) compute with ~20 torch kernels, an int64 argsort and several host
+ * round trips.  geom: [BN, D, fH, fW, 3] fp32 LiDAR-frame xyz (get_geometry's output, B = b samples of BN / b
+ * cameras); bx / dx: HOST float[3] first-cell centre and cell size; nx, ny, nz cell counts.
+ * Outputs (device int32; the caller sizes them for the worst case N' = BN*D*fH*fW points, n_cells = b*nz*nx*ny):
+ *   cell_of_point [N']            output cell (b*nz + z)*nx*ny + x*ny + y of every frustum point, -1 = outside
+ *   src [N']                      frustum indices of the kept points ordered by cell, ties in frustum order (first nk)
+ *   interval_starts [min(N',n_cells)+1], interval_cell [min(N',n_cells)]     CSR over src, one interval per hit cell
+ *   tile_starts [bevf_bev_pool_num_tiles()+1]
+ *   run_p0, run_len, cell_run_ids [N'], col_run_starts [BN*fW+1], cell_run_starts [min(N',n_cells)+1]
+ *                                 the ray-major run tables of bevf_bev_pool_fused_forward_runs
+ *   counts [3]                    nk, n_intervals, n_runs -- written on the device; nothing here waits for the host
+ */
+size_t bevf_bev_pool_tables_workspace_bytes(long long nprime, int b, int nz, int nx, int ny);
+int bevf_bev_pool_build_tables(const float *geom, int bn, int d, int fh, int fw, int b, const float *bx,
+                               const float *dx, int nx, int ny, int nz, int *cell_of_point, int *src,
+                               int *interval_starts, int *interval_cell, int *tile_starts, int *run_p0, int *run_len,
+                               int *col_run_starts, int *cell_run_ids, int *cell_run_starts, int *counts,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ *
  * Upstream of bev_pool: LiDAR depth image and its per-feature-cell histogram
  * ------------------------------------------------------------------------------------------------ */

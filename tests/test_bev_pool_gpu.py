@@ -197,3 +197,85 @@ def test_linearity_and_zero_cells_full_size():
     kept_w[tabs.src.long()] = 1.0
     total = ((d_t.double() * kept_w.view_as(d_t)).sum(1, keepdim=True) * c_t.double()).sum()
     np.testing.assert_allclose(float(out.double().sum()), float(total), rtol=1e-6)
+
+
+TABLE_FIELDS = ("src", "interval_starts", "interval_cell", "cell_of_point", "tile_starts", "run_p0", "run_len",
+                "col_run_starts", "cell_run_ids", "cell_run_starts")
+
+
+def _assert_tables_equal(dev_t, ref_t):
+    assert (dev_t.nk, dev_t.n_intervals, dev_t.n_runs) == (ref_t.nk, ref_t.n_intervals, ref_t.n_runs)
+    assert dev_t.use_runs == ref_t.use_runs
+    for f in TABLE_FIELDS:
+        a, b = getattr(dev_t, f), getattr(ref_t, f)
+        assert a.dtype == torch.int32 and a.shape == b.shape, f
+        assert torch.equal(a, b), f"table {f} differs"
+
+
+@pytest.mark.parametrize("case", ["small_b2", "config_A", "config_C_custom", "stress_D236_b2", "nz2_b2"])
+def test_device_built_tables_equal_bev_pool_aux_route(case):
+    """csrc/bev_tables.cu against the reference's bev_pool_aux formulation (depth_lss.py:118-176 + the interval
+    construction of bev_pool.py:158-166): every table bit for bit (integer work)."""
+    if case == "small_b2":
+        vt, geom, _, _ = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 1)
+    elif case == "config_C_custom":
+        vt, geom, _, _ = _view_case(1, 5, (48, 88), (384, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 6)
+    elif case == "stress_D236_b2":
+        vt, geom, _, _ = _view_case(2, 6, (32, 88), (256, 704), [1.0, 60.0, 0.25], 80, [-54.0, 54.0, 0.3], 7)
+    elif case == "nz2_b2":   # two Z slabs and two samples: rank order (x, y, z, b) != output-memory order (b, z, x, y)
+        vt = BaseViewTransform(8, 16, (64, 176), (8, 22), [-27.0, 27.0, 0.6], [-27.0, 27.0, 0.6], [-4.0, 4.0, 4.0],
+                               [1.0, 30.0, 1.0]).cuda()
+        rig = {k: torch.from_numpy(v).cuda() for k, v in synthetic.camera_rig(n_cams=3, image_size=(64, 176),
+                                                                             batch=2).items()}
+        geom = vt.get_geometry(**rig)
+    else:
+        vt, geom, _, _ = _view_case(1, 6, (32, 88), (256, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 0)
+    ref_t = vt.build_tables(geom, device_build=False)
+    dev_t = vt.build_tables(geom, device_build=True)
+    assert dev_t.nk > 0 and dev_t.n_runs > 0
+    _assert_tables_equal(dev_t, ref_t)
+    dev_again = vt.build_tables(geom)   # default for CUDA geometry; no atomics-order dependence
+    _assert_tables_equal(dev_again, ref_t)
+
+
+def test_device_built_tables_on_reference_golden_geometry(oracle_mod):
+    """The geometry the reference's own get_geometry produced (with extra_rots / extra_trans), its kept mask and
+    rank order: src must be the reference's kept[indices] up to the order inside one cell."""
+    g = golden("view_geometry.npz")
+    geom = torch.from_numpy(g["geom"]).cuda()
+    B = geom.shape[0]
+    nx = [int(v) for v in g["nx"]]
+    t = ops.BevPoolTables.from_geometry(geom, B, g["bx"].tolist(), g["dx"].tolist(), nx)
+    kept = g["kept"].reshape(-1)
+    np.testing.assert_array_equal((t.cell_of_point >= 0).cpu().numpy(), kept)
+    assert t.nk == int(kept.sum()) == g["geom_feats"].shape[0]
+    gf = g["geom_feats"]                                     # sorted (x, y, z, b) rows, rank order
+    cell_ref = (gf[:, 3] * nx[2] + gf[:, 2]) * (nx[0] * nx[1]) + gf[:, 0] * nx[1] + gf[:, 1]
+    cop = t.cell_of_point.cpu().numpy()
+    np.testing.assert_array_equal(np.sort(cop[cop >= 0]), np.sort(cell_ref))
+    src = t.src.cpu().numpy()
+    assert (np.diff(cop[src]) >= 0).all()                    # ordered by cell
+    same = cop[src][1:] == cop[src][:-1]
+    assert (np.diff(src)[same] > 0).all()                    # ties in frustum order
+    np.testing.assert_array_equal(np.unique(cell_ref), t.interval_cell.cpu().numpy())
+
+
+def test_device_built_tables_edge_values():
+    """Truncation toward zero keeps (-1, 0) in cell 0 (depth_lss.py:129 `.long()`); NaN / far-away points drop; an
+    all-outside frustum gives empty tables."""
+    vt = BaseViewTransform(8, 16, (64, 176), (8, 22), [-27.0, 27.0, 0.6], [-27.0, 27.0, 0.6], [-10.0, 10.0, 20.0],
+                           [1.0, 4.0, 1.0]).cuda()
+    geom = torch.full((1, 1, 3, 8, 22, 3), 1e9, device="cuda")
+    lo = float(vt.bx[0] - vt.dx[0] / 2)
+    geom[0, 0, 0, 0, 0] = torch.tensor([lo - 0.3, lo - 0.59, 0.0])   # u in (-1, 0) on x and y -> cell (0, 0)
+    geom[0, 0, 0, 1, 0] = torch.tensor([lo - 0.6001, lo, 0.0])       # u <= -1 -> dropped
+    geom[0, 0, 0, 2, 0] = torch.tensor([float("nan"), lo, 0.0])
+    geom[0, 0, 1, 0, 5] = torch.tensor([lo + 53.99, lo + 53.99, 9.9])  # last cell
+    ref_t = vt.build_tables(geom, device_build=False)
+    dev_t = vt.build_tables(geom, device_build=True)
+    _assert_tables_equal(dev_t, ref_t)
+    assert dev_t.nk == 2 and dev_t.interval_cell.tolist() == [0, 90 * 90 - 1]
+    empty = vt.build_tables(torch.full((1, 1, 3, 8, 22, 3), 1e9, device="cuda"), device_build=True)
+    assert (empty.nk, empty.n_intervals, empty.n_runs) == (0, 0, 0) and not empty.use_runs
+    out = vt.pool_fused(torch.rand(1, 3, 8, 22, device="cuda"), torch.rand(1, 16, 8, 22, device="cuda"), empty)
+    assert out.shape == (1, 16, 90, 90) and float(out.abs().sum()) == 0.0
