@@ -330,7 +330,7 @@ int bevf_spconv_gemm_f32(const float *feats, const float *weight_kio, const int 
                          const int *n_out_dev, int kv, int cin, int cout, const float *bias, const float *bn_scale,
                          const float *bn_shift, const float *residual, int relu, float *out, void *stream);
 /*
- * bf16 tensor-core path (TMA tile::gather4 -> tcgen05.mma, fp32 accumulation in TMEM): features bf16 [n_in, cin_pad] (cin_pad =
+ * bf16 tensor-core path (tcgen05.mma, fp32 accumulation in TMEM): features bf16 [n_in, cin_pad] (cin_pad =
  * bevf_spconv_tc_cin_pad(cin) in {16,32,64,128}, zero padded: bevf_spconv_cast_bf16), weights packed per tap into
  * the UMMA K-major core-matrix image (bevf_spconv_pack_weight_bf16, kv*cout*cin_pad bf16).  Cout in
  * {16,32,64,128}.  Writes fp32 (out_f32) and/or bf16 (out_bf16, feeds the next layer without a cast pass).  The
@@ -338,6 +338,12 @@ int bevf_spconv_gemm_f32(const float *feats, const float *weight_kio, const int 
  */
 int bevf_spconv_tc_cin_pad(int cin);
 int bevf_spconv_tc_supported(int cin, int cout);
+/* Which gather-GEMM kernel bevf_spconv_gemm_bf16 launches: 0 = operand tiles in shared memory ("SS" tcgen05.mma)
+ * everywhere, 1 (default) = operand rows in tensor memory ("TS" form, TMA-swizzled halo) for submanifold-shaped
+ * launches (kv == 27, n_in == output rows) and the SS kernel otherwise, 2 = TS everywhere it is instantiated.
+ * Results are bit-identical between the variants (same bf16 products, same fp32 accumulation order).  variant < 0
+ * only queries.  Returns the previous setting; process-wide (also env BEVFRONT_TC_TS at load time). */
+int bevf_spconv_tc_variant(int variant);
 int bevf_spconv_cast_bf16(const float *src, void *dst_bf16, int n, int cin, int cin_pad, const int *n_dev,
                           void *stream);
 int bevf_spconv_pack_weight_bf16(const float *weight_okc, void *weight_packed, int kv, int cin, int cout,

@@ -17,6 +17,10 @@ model = frontend.BEVFrontEnd(precision=precision).to(dev).eval()
 pts = torch.from_numpy(synthetic.lidar_sweeps(seed=0)).to(dev)
 feats, coords, _ = model.voxelize([pts])
 enc = model.pts_middle_encoder
+from bevfusion_3d_object_detection_b200._lib import lib  # noqa: E402
+if len(sys.argv) > 2:
+    lib().bevf_spconv_tc_variant(int(sys.argv[2]))   # 0 = SS kernel, 1 = default, 2 = TS wherever instantiated
+print("tc variant", lib().bevf_spconv_tc_variant(-1))
 with torch.no_grad():
     for _ in range(3):
         enc(feats, coords, 1)

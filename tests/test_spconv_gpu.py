@@ -184,6 +184,65 @@ def test_conv_bf16_tensor_core_matches_oracle(oracle_mod, cin, cout, ksize, subm
     np.testing.assert_allclose(out._bf16.float().cpu().numpy(), got, rtol=1e-2, atol=1e-2 * scale)
 
 
+@pytest.fixture
+def tc_variant():
+    """Select the gather-GEMM kernel of the bf16 path (0 = SS: operand tiles in smem, 1 = default, 2 = TS: operand
+    rows in tensor memory wherever instantiated) and restore the setting afterwards."""
+    from bevfusion_3d_object_detection_b200._lib import lib
+
+    prev = lib().bevf_spconv_tc_variant(-1)
+    yield lambda v: lib().bevf_spconv_tc_variant(int(v))
+    lib().bevf_spconv_tc_variant(prev)
+
+
+@pytest.mark.parametrize("c,n,grid,sort", [
+    (16, 100, (12, 12, 6), True),          # a single partial tile
+    (128, 300, (12, 12, 6), True),
+    (32, 9000, (40, 40, 11), True),        # dense neighbourhoods, short last tile
+    (64, 3000, (20, 18, 9), False),        # unsorted rows: ranges exceed the halo -> global-load fallback
+    (16, 90000, (256, 256, 16), True),     # two CTAs per SM, several tiles per CTA: ring / accumulator phases wrap
+    (32, 90000, (256, 256, 16), True),
+    (64, 50000, (192, 192, 16), True),
+    (128, 45000, (160, 160, 16), True),    # MT = 1, streamed weights, two column slabs per halo row
+])
+def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, n, grid, sort):
+    """The TS-form kernel (operand rows written to tensor memory from a TMA-swizzled halo) against the SS-form
+    kernel bit for bit (same bf16 products, same accumulation order) and against the oracle on bf16-rounded
+    operands; residual + folded-BN + ReLU epilogue included."""
+    rng = np.random.default_rng(c + n)
+    shape, batch = list(grid), 1
+    idx = random_sites(rng, n, batch, shape, sort=sort)
+    feats = rng.standard_normal((idx.shape[0], c)).astype(np.float32)
+    w = (rng.standard_normal((c, 3, 3, 3, c)) / np.sqrt(27 * c)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    shift = (rng.standard_normal(c) * 0.1).astype(np.float32)
+    res = rng.standard_normal((idx.shape[0], c)).astype(np.float32)
+    x = tensor_from(idx, feats, shape, batch)
+    datas = Fsp.get_indice_pairs(x, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True)
+    packed = Fsp.pack_weight_bf16(torch.from_numpy(w).cuda())
+    t = lambda a: torch.from_numpy(a).cuda()
+    outs = []
+    for variant in (0, 2):
+        tc_variant(variant)
+        o, ob = Fsp.implicit_gemm(t(feats), datas.pair_fwd, datas.n_out, packed, 27, c, c, precision="bf16",
+                                  bn_scale=t(scale), bn_shift=t(shift), residual=t(res), relu=True, want_bf16=True)
+        torch.cuda.synchronize()
+        outs.append((o.cpu().numpy(), ob.float().cpu().numpy()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    fq = torch.from_numpy(feats).bfloat16().float().numpy()
+    wq = torch.from_numpy(w).bfloat16().float().numpy()
+    # the scalar oracle on the first and last rows (all rows are covered by the bit-wise comparison above)
+    pair = datas.pair_fwd.cpu().numpy()[:, :datas.n_out]
+    for sl in (slice(0, min(3000, datas.n_out)), slice(max(0, datas.n_out - 1500), datas.n_out)):
+        ps = np.ascontiguousarray(pair[:, sl])
+        ref = oracle_mod.spconv_gemm(fq, wq, ps)
+        l1 = oracle_mod.spconv_gemm(np.abs(fq), np.abs(wq), ps)
+        ref = np.maximum(ref * scale + shift + res[sl], 0.0)
+        err = np.abs(outs[1][0][sl] - ref)
+        assert (err <= 1e-5 * np.abs(ref) + 4e-6 * (l1 * scale + np.abs(shift) + np.abs(res[sl]))).all(), float(err.max())
+
+
 def test_fused_epilogue_matches_unfused(oracle_mod):
     """SparseBasicBlock in eval mode (BN + residual + ReLU folded into the GEMM epilogue) == the oracle chain
     conv -> bn -> relu -> conv -> bn -> +identity -> relu (sparse_block.py:137-154)."""
