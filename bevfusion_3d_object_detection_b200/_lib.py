@@ -32,8 +32,8 @@ def lib():
     """Load (building first if the sources are newer) libbevfront_b200.so.  Fails loudly."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if _build.is_stale():
+        path = os.environ.get("BEVFRONT_LIB") or _build.LIB   # BEVFRONT_LIB: an instrumented debug build of the same ABI
+        if path == _build.LIB and _build.is_stale():
             if os.environ.get("BEVFRONT_NO_BUILD") and not os.path.exists(path):
                 raise BevfError(f"{path} is missing and BEVFRONT_NO_BUILD is set")
             try:
