@@ -21,13 +21,13 @@ with torch.no_grad():
     lib().bevf_debug_ts_prof(buf)
     model.pts_middle_encoder(feats, coords, 1)
     lib().bevf_debug_ts_prof(buf)
-names = ["b_tot", "b_halo", "b_lds", "b_empty", "b_st", "b_rot", "b_warps", "-", "m_tot", "m_acc", "m_bfull", "m_full",
+names = ["b_tot", "b_halo", "b_lds", "b_empty", "b_st", "b_rot", "b_warps", "b_grp", "m_tot", "m_acc", "m_bfull", "m_full",
          "m_warps", "m_items", "e_wait", "e_work"]
 for ci, c in enumerate((16, 32, 64, 128)):
     v = [buf[ci * 16 + i] for i in range(16)]
     bw, mw = max(v[6], 1), max(v[12], 1)
     print(f"cin {c}: builder warps {v[6]} MMA warps {v[12]} items {v[13]}")
-    print("  builder per warp (kclk): " + ", ".join(f"{n}={v[i] / bw / 1e3:.1f}" for i, n in enumerate(names[:6])))
+    print("  builder per warp (kclk): " + ", ".join(f"{n}={v[i] / bw / 1e3:.1f}" for i, n in list(enumerate(names[:6])) + [(7, "b_grp")]))
     print("  mma per warp (kclk): " + ", ".join(f"{names[i]}={v[i] / mw / 1e3:.1f}" for i in (8, 9, 10, 11))
           + f", per item: tot={v[8] / max(v[13], 1):.0f} full_wait={v[11] / max(v[13], 1):.0f}")
     print(f"  epilogue warp0 per CTA (kclk): wait={v[14] / mw / 1e3:.1f} work={v[15] / mw / 1e3:.1f}")
