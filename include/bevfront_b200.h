@@ -339,10 +339,11 @@ int bevf_spconv_gemm_f32(const float *feats, const float *weight_kio, const int 
 int bevf_spconv_tc_cin_pad(int cin);
 int bevf_spconv_tc_supported(int cin, int cout);
 /* Which gather-GEMM kernel bevf_spconv_gemm_bf16 launches: 0 = operand tiles in shared memory ("SS" tcgen05.mma)
- * everywhere, 1 (default) = operand rows in tensor memory ("TS" form, TMA-swizzled halo) for submanifold-shaped
- * launches (kv == 27, n_in == output rows) and the SS kernel otherwise, 2 = TS everywhere it is instantiated.
- * Results are bit-identical between the variants (same bf16 products, same fp32 accumulation order).  variant < 0
- * only queries.  Returns the previous setting; process-wide (also env BEVFRONT_TC_TS at load time). */
+ * everywhere; 1 (default; 2 is a synonym) = operand rows in tensor memory ("TS" form, TMA-swizzled halo, global loads
+ * where the row range does not fit) for the channel pairs it is instantiated for -- 16->16, 32->32, 64->64, 128->128,
+ * 16->32, 32->64, 64->128 -- and the SS kernel for the rest.  Results are bit-identical between the variants (same
+ * bf16 products, same fp32 accumulation order).  variant < 0 only queries.  Returns the previous setting;
+ * process-wide (also env BEVFRONT_TC_TS at load time). */
 int bevf_spconv_tc_variant(int variant);
 int bevf_spconv_cast_bf16(const float *src, void *dst_bf16, int n, int cin, int cin_pad, const int *n_dev,
                           void *stream);

@@ -186,8 +186,8 @@ def test_conv_bf16_tensor_core_matches_oracle(oracle_mod, cin, cout, ksize, subm
 
 @pytest.fixture
 def tc_variant():
-    """Select the gather-GEMM kernel of the bf16 path (0 = SS: operand tiles in smem, 1 = default, 2 = TS: operand
-    rows in tensor memory wherever instantiated) and restore the setting afterwards."""
+    """Select the gather-GEMM kernel of the bf16 path (0 = SS: operand tiles in smem, 1 = default = TS: operand rows in
+    tensor memory wherever instantiated) and restore the setting afterwards."""
     from bevfusion_3d_object_detection_b200._lib import lib
 
     prev = lib().bevf_spconv_tc_variant(-1)
@@ -222,7 +222,7 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
     packed = Fsp.pack_weight_bf16(torch.from_numpy(w).cuda())
     t = lambda a: torch.from_numpy(a).cuda()
     outs = []
-    for variant in (0, 2):
+    for variant in (0, 1):
         tc_variant(variant)
         o, ob = Fsp.implicit_gemm(t(feats), datas.pair_fwd, datas.n_out, packed, 27, c, c, precision="bf16",
                                   bn_scale=t(scale), bn_shift=t(shift), residual=t(res), relu=True, want_bf16=True)
@@ -241,6 +241,37 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
         ref = np.maximum(ref * scale + shift + res[sl], 0.0)
         err = np.abs(outs[1][0][sl] - ref)
         assert (err <= 1e-5 * np.abs(ref) + 4e-6 * (l1 * scale + np.abs(shift) + np.abs(res[sl]))).all(), float(err.max())
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride,padding,n,grid", [
+    (16, 32, (3, 3, 3), 2, 1, 60000, (192, 192, 16)),
+    (32, 64, (3, 3, 3), 2, 1, 50000, (160, 160, 16)),
+    (64, 128, (3, 3, 3), 2, (1, 1, 0), 30000, (128, 128, 11)),
+    (128, 128, (1, 1, 3), (1, 1, 2), 0, 30000, (128, 128, 5)),     # conv_out: kv = 3
+])
+def test_bf16_ts_kernel_strided_matches_ss_kernel(tc_variant, cin, cout, ksize, stride, padding, n, grid):
+    """Strided (regular) sparse convs through the TS kernel: bit-identical to the SS kernel, which
+    test_conv_bf16_tensor_core_matches_oracle pins to the oracle."""
+    rng = np.random.default_rng(cin + cout + n)
+    shape, batch = list(grid), 1
+    idx = random_sites(rng, n, batch, shape, sort=True)
+    feats = rng.standard_normal((idx.shape[0], cin)).astype(np.float32)
+    kv = int(np.prod(ksize))
+    w = (rng.standard_normal((cout, *ksize, cin)) / np.sqrt(kv * cin)).astype(np.float32)
+    x = tensor_from(idx, feats, shape, batch)
+    st3 = (stride,) * 3 if isinstance(stride, int) else stride
+    pd3 = (padding,) * 3 if isinstance(padding, int) else padding
+    datas = Fsp.get_indice_pairs(x, ksize, st3, pd3, (1, 1, 1), False)
+    packed = Fsp.pack_weight_bf16(torch.from_numpy(w).cuda())
+    outs = []
+    for variant in (0, 1):
+        tc_variant(variant)
+        o, _ = Fsp.implicit_gemm(torch.from_numpy(feats).cuda(), datas.pair_fwd, datas.n_out, packed, kv, cin, cout,
+                                 precision="bf16", relu=True)
+        torch.cuda.synchronize()
+        outs.append(o.cpu().numpy())
+    assert datas.n_out > 20000 and np.abs(outs[0]).max() > 0
+    np.testing.assert_array_equal(outs[0], outs[1])
 
 
 def test_fused_epilogue_matches_unfused(oracle_mod):
