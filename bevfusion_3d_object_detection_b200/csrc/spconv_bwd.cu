@@ -1,0 +1,157 @@
+// spconv_bwd.cu -- backward of the sparse convolution (training: BASELINE configs[2]).
+//
+//   forward   out[j, :]      = sum_k feats[pair_fwd[k, j], :] @ W[k]                      (W[k] is [Cin, Cout])
+//   dgrad     d_feats[i, :]  = sum_k d_out[pair_bwd[k, i], :] @ W[k]^T    pair_bwd[k, pair_fwd[k, j]] = j
+//   wgrad     d_W[k]         = sum_j feats[pair_fwd[k, j], :]^T (x) d_out[j, :]
+//
+// spconv does the same through its implicit-GEMM backward kernels (reference call site
+// projects/SparseConvolution/sparse_functional.py: ConvGemmOps.implicit_gemm with the bwd pair tables); here the
+// data gradient IS a forward gather-GEMM over the inverse rulebook (bevf_spconv_pair_bwd, this file) with the weights
+// re-packed transposed, so it runs on the same fp32 / tcgen05 kernels as the forward, and the weight gradient is a
+// tiled fp32 outer-product reduction (64 x 64 output tile per CTA, rows streamed through shared memory, split over
+// row ranges, fp32 atomics into d_W).
+//
+// An input row feeds at most one output row per tap in every convolution geometry (out = (in + pad - k*dil) / stride is
+// a function of (in, k)), so the inverse rulebook is a plain scatter without conflicts.
+#include "common.cuh"
+
+namespace {
+
+__global__ void pair_bwd_fill_kernel(int *__restrict__ pair_bwd, long long total) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) pair_bwd[t] = -1;
+}
+
+__global__ void pair_bwd_scatter_kernel(const int *__restrict__ pair_fwd, int ld, int n_out_host,
+                                        const int *__restrict__ n_out_dev, int kv, int *__restrict__ pair_bwd,
+                                        int ld_in, int n_in) {
+  const int n_out = n_out_dev ? min(*n_out_dev, ld) : n_out_host;
+  const long long total = (long long)kv * n_out;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t / n_out), j = (int)(t - (long long)k * n_out);
+    const int i = __ldg(pair_fwd + (size_t)k * ld + j);
+    if (i >= 0 && i < n_in) pair_bwd[(size_t)k * ld_in + i] = j;
+  }
+}
+
+constexpr int WT = 64;        // d_W tile: WT output channels x WT input channels per CTA
+constexpr int WR = 16;        // rows per shared-memory step
+constexpr int kWThreads = 256;
+
+// grid: (row splits, kv, cout tiles * cin tiles).  d_w layout [Cout, kv, Cin] (the spconv-2.x parameter layout).
+__global__ void __launch_bounds__(kWThreads)
+    spconv_wgrad_f32_kernel(const float *__restrict__ feats, const float *__restrict__ d_out,
+                            const int *__restrict__ pair_fwd, int ld, int n_out_host, const int *__restrict__ n_out_dev,
+                            int kv, int cin, int cout, int rows_per_split, float *__restrict__ d_w) {
+  __shared__ __align__(16) float Gs[WR][WT + 4];   // d_out rows   [r][co]
+  __shared__ __align__(16) float Xs[WR][WT + 4];   // gathered in  [r][ci]
+  __shared__ int any_valid;
+  const int n_out = n_out_dev ? min(*n_out_dev, ld) : n_out_host;
+  const int k = blockIdx.y;
+  const int cin_tiles = (cin + WT - 1) / WT;
+  const int co0 = ((int)blockIdx.z / cin_tiles) * WT, ci0 = ((int)blockIdx.z % cin_tiles) * WT;
+  const int j_begin = blockIdx.x * rows_per_split;
+  const int j_end = min(j_begin + rows_per_split, n_out);
+  if (j_begin >= j_end) return;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;          // thread tile: co = co0 + ty*4 + a, ci = ci0 + tx*4 + b
+  const int lr = tid >> 4, lc = (tid & 15) * 4;    // loader: row lr, 4 channels from lc
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  bool touched = false;
+
+  for (int j0 = j_begin; j0 < j_end; j0 += WR) {
+    const int j = j0 + lr;
+    int idx = -1;
+    if (j < j_end) idx = __ldg(pair_fwd + (size_t)k * ld + j);
+    if (tid == 0) any_valid = 0;
+    __syncthreads();
+    if (idx >= 0 && (tid & 15) == 0) any_valid = 1;
+    float g[4] = {0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (idx >= 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (co0 + lc + c < cout) g[c] = __ldg(d_out + (size_t)j * cout + co0 + lc + c);
+        if (ci0 + lc + c < cin) x[c] = __ldg(feats + (size_t)idx * cin + ci0 + lc + c);
+      }
+    }
+    *reinterpret_cast<float4 *>(&Gs[lr][lc]) = make_float4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<float4 *>(&Xs[lr][lc]) = make_float4(x[0], x[1], x[2], x[3]);
+    __syncthreads();
+    if (any_valid) {
+      touched = true;
+#pragma unroll
+      for (int r = 0; r < WR; ++r) {
+        const float4 gv = *reinterpret_cast<const float4 *>(&Gs[r][ty * 4]);
+        const float4 xv = *reinterpret_cast<const float4 *>(&Xs[r][tx * 4]);
+        const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], xa[b], acc[a][b]);
+      }
+    }
+    __syncthreads();
+  }
+  if (!touched) return;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int co = co0 + ty * 4 + a;
+    if (co >= cout) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ci = ci0 + tx * 4 + b;
+      if (ci < cin && acc[a][b] != 0.f) atomicAdd(d_w + ((size_t)co * kv + k) * cin + ci, acc[a][b]);
+    }
+  }
+}
+
+}  // namespace
+
+BEVF_API int bevf_spconv_pair_bwd(const int *pair_fwd, int ld, int n_out, const int *n_out_dev, int kv, int *pair_bwd,
+                                  int ld_in, int n_in, void *stream) {
+  BEVF_CHECK_ARG(kv > 0 && ld >= n_out && n_out >= 0 && ld_in >= n_in && n_in >= 0, "bad rulebook shape");
+  if (n_in == 0 || ld_in == 0) return BEVF_OK;
+  BEVF_CHECK_ARG(pair_bwd && (pair_fwd || n_out == 0), "NULL rulebook");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total_in = (long long)kv * ld_in;
+  pair_bwd_fill_kernel<<<bevf::ceil_div(total_in, 256), 256, 0, st>>>(pair_bwd, total_in);
+  BEVF_CHECK_LAUNCH();
+  const int rows = n_out_dev ? ld : n_out;
+  if (rows == 0) return BEVF_OK;
+  const long long total = (long long)kv * rows;
+  const int grid = (int)((total + 255) / 256 < 148LL * 16 ? (total + 255) / 256 : 148LL * 16);
+  pair_bwd_scatter_kernel<<<grid, 256, 0, st>>>(pair_fwd, ld, n_out, n_out_dev, kv, pair_bwd, ld_in, n_in);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_spconv_wgrad_f32(const float *feats, const float *d_out, const int *pair_fwd, int ld, int n_out,
+                                   const int *n_out_dev, int kv, int cin, int cout, float *d_weight_okc, void *stream) {
+  BEVF_CHECK_ARG(kv > 0 && cin > 0 && cout > 0 && ld >= n_out && n_out >= 0, "bad wgrad shape");
+  BEVF_CHECK_ARG(d_weight_okc, "NULL weight gradient");
+  cudaStream_t st = (cudaStream_t)stream;
+  BEVF_CHECK_CUDA(cudaMemsetAsync(d_weight_okc, 0, sizeof(float) * (size_t)cout * kv * cin, st));
+  const int rows = n_out_dev ? ld : n_out;
+  if (rows == 0) return BEVF_OK;
+  BEVF_CHECK_ARG(feats && d_out && pair_fwd, "NULL tensor");
+  // enough row splits to fill the machine a few times over, at least 512 rows each
+  const int tiles = bevf::ceil_div(cout, WT) * bevf::ceil_div(cin, WT);
+  int splits = bevf::ceil_div(4 * bevf::kNumSMs, kv * tiles);
+  const int max_splits = bevf::ceil_div(rows, 512);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int rows_per_split = bevf::ceil_div(rows, splits);
+  rows_per_split = bevf::ceil_div(rows_per_split, WR) * WR;
+  splits = bevf::ceil_div(rows, rows_per_split);
+  dim3 grid(splits, kv, tiles);
+  spconv_wgrad_f32_kernel<<<grid, kWThreads, 0, st>>>(feats, d_out, pair_fwd, ld, n_out, n_out_dev, kv, cin, cout,
+                                                     rows_per_split, d_weight_okc);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}

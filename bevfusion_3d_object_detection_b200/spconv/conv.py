@@ -28,8 +28,9 @@ def get_default_precision():
 
 
 class _SparseConvFunction(torch.autograd.Function):
-    """Forward on libbevfront_b200; backward (training, SURVEY configs[2]) as gather / matmul / index_add over
-    the same rulebook.  The backward is functional plumbing in torch ops, not a tuned kernel."""
+    """Forward and backward on libbevfront_b200 (training, SURVEY configs[2]).  The data gradient is the forward
+    gather-GEMM over the inverse rulebook with transposed weights (same fp32 / tcgen05 kernels as the forward), the
+    weight gradient a tiled fp32 outer-product reduction (csrc/spconv_bwd.cu); no host round trips."""
 
     @staticmethod
     def forward(ctx, features, weight, bias, pair_fwd, n_out, packed, precision):
@@ -38,6 +39,8 @@ class _SparseConvFunction(torch.autograd.Function):
         out, _ = Fsp.implicit_gemm(features, pair_fwd, n_out, packed, kv, cin, cout, precision=precision, bias=bias)
         ctx.save_for_backward(features, weight, pair_fwd)
         ctx.has_bias = bias is not None
+        ctx.precision = precision
+        ctx.n_out = n_out
         return out
 
     @staticmethod
@@ -45,23 +48,24 @@ class _SparseConvFunction(torch.autograd.Function):
         features, weight, pair_fwd = ctx.saved_tensors
         cout, cin = weight.shape[0], weight.shape[-1]
         kv = pair_fwd.shape[0]
-        w = weight.reshape(cout, kv, cin)
-        grad_out = grad_out.contiguous()
-        g_feat = torch.zeros_like(features) if ctx.needs_input_grad[0] else None
-        g_w = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
-        for k in range(kv):
-            idx = pair_fwd[k]
-            sel = torch.nonzero(idx >= 0, as_tuple=False).squeeze(1)
-            if sel.numel() == 0:
-                continue
-            rows = idx[sel].long()
-            go = grad_out[sel]
-            if g_feat is not None:
-                g_feat.index_add_(0, rows, go @ w[:, k, :])
-            if g_w is not None:
-                g_w[:, k, :] = go.t() @ features[rows]
+        n_in, n_out = features.shape[0], ctx.n_out
+        grad_out = grad_out.contiguous().float()
+        g_feat = g_w = None
+        if ctx.needs_input_grad[0]:
+            if n_in == 0 or n_out == 0:
+                g_feat = torch.zeros_like(features)
+            else:
+                # W^T per tap in the parameter layout of a (Cout -> Cin) convolution: [Cin, kD, kH, kW, Cout]
+                wt = weight.detach().reshape(cout, kv, cin).permute(2, 1, 0).contiguous().view(
+                    cin, *weight.shape[1:-1], cout)
+                prec = ctx.precision if (ctx.precision == "fp32" or Fsp.tc_supported(cout, cin)) else "fp32"
+                packed_t = Fsp.pack_weight_bf16(wt) if prec == "bf16" else Fsp.pack_weight_f32(wt)
+                pb = Fsp.pair_bwd(pair_fwd, n_out, n_in)
+                g_feat, _ = Fsp.implicit_gemm(grad_out, pb, n_in, packed_t, kv, cout, cin, precision=prec)
+        if ctx.needs_input_grad[1]:
+            g_w = Fsp.wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
         g_b = grad_out.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return g_feat, (g_w.reshape(weight.shape) if g_w is not None else None), g_b, None, None, None, None
+        return g_feat, g_w, g_b, None, None, None, None
 
 
 class SparseConvolution(SparseModule):

@@ -115,6 +115,29 @@ def cast_features_bf16(features, cin_pad):
     return out
 
 
+def pair_bwd(pair_fwd, n_out, n_in):
+    """Inverse rulebook [kv, n_in]: pair_bwd[k, i] = j where pair_fwd[k, j] = i, -1 elsewhere."""
+    kv = pair_fwd.shape[0]
+    out = torch.empty((kv, max(n_in, 1)), dtype=torch.int32, device=pair_fwd.device)
+    ld = pair_fwd.stride(0) if pair_fwd.shape[1] > 0 else max(n_out, 1)
+    with torch.cuda.device(pair_fwd.device):
+        check(lib().bevf_spconv_pair_bwd(ptr(pair_fwd), int(ld), int(n_out), None, int(kv), ptr(out), int(out.stride(0)),
+                                         int(n_in), cur_stream(pair_fwd.device)))
+    return out[:, :n_in]
+
+
+def wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout):
+    """d_weight [Cout, kv, Cin] fp32 = sum over valid pairs of grad_out[j]^T (x) features[pair_fwd[k, j]]."""
+    f = features.detach().contiguous().float()
+    g = grad_out.detach().contiguous().float()
+    out = torch.empty((cout, kv, cin), dtype=torch.float32, device=f.device)
+    ld = pair_fwd.stride(0) if pair_fwd.shape[1] > 0 else max(n_out, 1)
+    with torch.cuda.device(f.device):
+        check(lib().bevf_spconv_wgrad_f32(ptr(f), ptr(g), ptr(pair_fwd), int(ld), int(n_out), None, int(kv), int(cin),
+                                          int(cout), ptr(out), cur_stream(f.device)))
+    return out
+
+
 def tc_supported(cin, cout):
     return bool(lib().bevf_spconv_tc_supported(int(cin), int(cout)))
 

@@ -330,6 +330,20 @@ int bevf_spconv_gemm_f32(const float *feats, const float *weight_kio, const int 
                          const int *n_out_dev, int kv, int cin, int cout, const float *bias, const float *bn_scale,
                          const float *bn_shift, const float *residual, int relu, float *out, void *stream);
 /*
+ * Backward of the sparse convolution (training).  bevf_spconv_pair_bwd inverts a rulebook: pair_bwd[k, i] = j where
+ * pair_fwd[k, j] = i (-1 elsewhere; [kv, ld_in], fully written) -- an input row feeds at most one output row per tap.
+ * The data gradient is then the forward gather-GEMM over pair_bwd with the weights transposed
+ * (d_feats = gemm(d_out, pack(W^T), pair_bwd): bevf_spconv_gemm_f32 / _bf16), which is what spconv's implicit-GEMM
+ * backward computes (reference call site projects/SparseConvolution/sparse_functional.py:287-314, ConvGemmOps).
+ * bevf_spconv_wgrad_f32: d_weight[Cout, kv, Cin] = sum_j d_out[j, :]^T (x) feats[pair_fwd[k, j], :] in fp32 (the
+ * buffer is zeroed first; row ranges are reduced with fp32 atomics, so the last bits depend on scheduling).
+ */
+int bevf_spconv_pair_bwd(const int *pair_fwd, int ld, int n_out, const int *n_out_dev, int kv, int *pair_bwd, int ld_in,
+                         int n_in, void *stream);
+int bevf_spconv_wgrad_f32(const float *feats, const float *d_out, const int *pair_fwd, int ld, int n_out,
+                          const int *n_out_dev, int kv, int cin, int cout, float *d_weight_okc, void *stream);
+
+/*
  * bf16 tensor-core path (tcgen05.mma, fp32 accumulation in TMEM): features bf16 [n_in, cin_pad] (cin_pad =
  * bevf_spconv_tc_cin_pad(cin) in {16,32,64,128}, zero padded: bevf_spconv_cast_bf16), weights packed per tap into
  * the UMMA K-major core-matrix image (bevf_spconv_pack_weight_bf16, kv*cout*cin_pad bf16).  Cout in

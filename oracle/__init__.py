@@ -271,6 +271,30 @@ def spconv_gemm(feats, weight, pair_fwd, bias=None, acc_double=True):
     return out
 
 
+def spconv_backward(feats, weight, pair_fwd, grad_out):
+    """Gradients of spconv_gemm (numpy, float64): the transpose of the forward restatement above -- spconv's backward
+    lives in the third-party package (not in /root/reference), so this is the definition
+    d_feats[pair[k, j]] += grad_out[j] @ W[:, k, :],  d_W[:, k, :] = grad_out[valid]^T @ feats[pair[k, valid]].
+    weight [Cout, kD, kH, kW, Cin] -> (d_feats [n_in, Cin], d_weight like weight)."""
+    feats = np.asarray(feats, np.float64)
+    grad_out = np.asarray(grad_out, np.float64)
+    w = np.asarray(weight, np.float64)
+    cout, cin = w.shape[0], w.shape[-1]
+    kv = int(np.prod(w.shape[1:-1]))
+    w3 = w.reshape(cout, kv, cin)
+    d_feats = np.zeros_like(feats)
+    d_w = np.zeros_like(w3)
+    pair_fwd = np.asarray(pair_fwd)
+    for k in range(kv):
+        valid = np.nonzero(pair_fwd[k] >= 0)[0]
+        if valid.size == 0:
+            continue
+        rows = pair_fwd[k][valid]
+        np.add.at(d_feats, rows, grad_out[valid] @ w3[:, k, :])
+        d_w[:, k, :] = grad_out[valid].T @ feats[rows]
+    return d_feats, d_w.reshape(w.shape)
+
+
 def sparse_to_dense(feats, indices, batch_size, spatial_shape):
     feats = _f32(feats)
     n, c = feats.shape

@@ -433,3 +433,52 @@ def test_training_backward_matches_dense_autograd():
     ref.backward(g)
     np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(conv.weight.grad.cpu().numpy(), w.grad.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cin,cout,ksize,subm,stride,padding,n,precision", [
+    (16, 16, (3, 3, 3), True, 1, 1, 3000, "fp32"),
+    (16, 32, (3, 3, 3), False, 2, 1, 3000, "fp32"),          # strided: the inverse rulebook is not a tap flip
+    (96, 72, (3, 3, 3), True, 1, 1, 1500, "fp32"),           # 2 x 2 wgrad tiles with ragged edges
+    (128, 128, (1, 1, 3), False, (1, 1, 2), 0, 2000, "fp32"),
+    (5, 16, (3, 3, 3), True, 1, 1, 2000, "fp32"),
+    (64, 64, (3, 3, 3), True, 1, 1, 2500, "bf16"),           # data gradient on the tcgen05 kernels
+    (32, 64, (3, 3, 3), False, 2, 1, 3000, "bf16"),          # 64 -> 32 data gradient: SS kernel
+])
+def test_conv_backward_matches_oracle(oracle_mod, cin, cout, ksize, subm, stride, padding, n, precision):
+    """Data and weight gradients through the C ABI (inverse rulebook + gather-GEMM with transposed weights; tiled
+    fp32 wgrad) against the oracle's transpose of the forward restatement."""
+    rng = np.random.default_rng(cin * 7 + cout)
+    shape, batch = [20, 18, 9], 2
+    idx, feats, w, b, conv = _conv_case(rng, cin, cout, ksize, n, shape, batch, subm, stride, padding, False)
+    conv.precision = precision
+    x = torch.from_numpy(feats).cuda().requires_grad_(True)
+    out = conv(spconv.SparseConvTensor(x, torch.from_numpy(idx).cuda(), shape, batch))
+    g = rng.standard_normal(tuple(out.features.shape)).astype(np.float32)
+    out.features.backward(torch.from_numpy(g).cuda())
+    _, o_pair, _ = oracle_mod.spconv_rulebook(idx, shape, ksize, stride, padding, 1, subm)
+    d_feats, d_w = oracle_mod.spconv_backward(feats, w, o_pair, g)
+    l1_f, l1_w = oracle_mod.spconv_backward(np.abs(feats), np.abs(w), o_pair, np.abs(g))
+    got_f, got_w = x.grad.cpu().numpy(), conv.weight.grad.cpu().numpy()
+    assert got_f.shape == d_feats.shape and got_w.shape == d_w.shape
+    # weight gradient is always fp32 (fp32 atomics across row ranges: order-of-summation noise only)
+    assert (np.abs(got_w - d_w) <= 1e-5 * np.abs(d_w) + 2e-6 * l1_w).all(), float(np.abs(got_w - d_w).max())
+    if precision == "fp32":
+        assert (np.abs(got_f - d_feats) <= 1e-5 * np.abs(d_feats) + 1e-6 * l1_f).all(), float(np.abs(got_f - d_feats).max())
+    else:
+        assert np.abs(got_f - d_feats).max() <= RTOL_BF16 * np.abs(d_feats).max()
+
+
+def test_pair_bwd_is_the_inverse_rulebook(oracle_mod):
+    rng = np.random.default_rng(5)
+    shape, batch = [24, 20, 9], 2
+    idx = random_sites(rng, 3000, batch, shape)
+    x = tensor_from(idx, np.zeros((idx.shape[0], 4), np.float32), shape, batch)
+    for subm, stride in ((True, (1, 1, 1)), (False, (2, 2, 2))):
+        d = Fsp.get_indice_pairs(x, (3, 3, 3), stride, (1, 1, 1), (1, 1, 1), subm)
+        pf = d.pair_fwd.cpu().numpy()[:, :d.n_out]
+        pb = Fsp.pair_bwd(d.pair_fwd, d.n_out, idx.shape[0]).cpu().numpy()
+        ref = np.full_like(pb, -1)
+        for k in range(pf.shape[0]):
+            v = np.nonzero(pf[k] >= 0)[0]
+            ref[k, pf[k][v]] = v
+        np.testing.assert_array_equal(pb, ref)
