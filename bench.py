@@ -441,6 +441,52 @@ def run_b200(args, rank, world, local_rank):
             timing="CUDA graph of %d calls each; not part of the timed frame step" % RING)
     except Exception as exc:
         print(f"[bench] depth-prep timing unavailable: {exc}", file=sys.stderr)
+    # ---- configs[2] (training): forward + backward of the sparse encoder and of the fused bev_pool, one frame, eager
+    try:
+        from bevfusion_3d_object_detection_b200.sparse_encoder import NUSCENES_ENCODER_CFG, BEVFusionSparseEncoder
+
+        enc_t = BEVFusionSparseEncoder(**NUSCENES_ENCODER_CFG).to(dev)   # a separate copy: train-mode BN updates its stats
+        enc_t.load_state_dict(model.pts_middle_encoder.state_dict())
+        for m_ in enc_t.modules():
+            if hasattr(m_, "precision") and hasattr(m_, "indice_key"):
+                m_.precision = args.precision
+        enc_t.train()
+        x_t = feats.detach().clone().requires_grad_(True)
+        f0 = dev_frames[0]
+        d_t, c_t = f0["depth"].detach().clone().requires_grad_(True), f0["ctx"].detach().clone().requires_grad_(True)
+
+        def enc_step():
+            for p_ in enc_t.parameters():
+                p_.grad = None
+            x_t.grad = None
+            enc_t(x_t, coords, 1).sum().backward()
+
+        def pool_step():
+            d_t.grad = None
+            c_t.grad = None
+            model.extract_img_bev(d_t, c_t, tables).sum().backward()
+
+        def ev_ms(fn, reps):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        with torch.enable_grad():
+            ms_enc_t = ev_ms(enc_step, 3)
+            ms_pool_t = ev_ms(pool_step, 3)
+        stages["training"] = dict(sparse_encoder_fwd_bwd_ms=ms_enc_t, bev_pool_fused_fwd_bwd_ms=ms_pool_t,
+                                  timing="eager module path, train-mode BatchNorm1d, one frame, CUDA events; data "
+                                         "gradient on the forward GEMM kernels, fp32 weight gradient")
+        del enc_t, x_t, d_t, c_t
+    except Exception as exc:
+        print(f"[bench] training-stage timing unavailable: {exc}", file=sys.stderr)
     # ---- upstream "next" row: the pooling tables from the frustum geometry, device-side vs the
     #      reference's bev_pool_aux formulation (argsort + masked gathers); per calibration, so outside the frame step
     try:

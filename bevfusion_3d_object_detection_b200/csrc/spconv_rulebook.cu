@@ -214,6 +214,21 @@ __global__ void __launch_bounds__(256)
   dense[((size_t)q.x * c + ch) * vol + ((size_t)q.y * g.y + q.z) * g.z + q.w] = feats[t];
 }
 
+// backward of dense() / of the fused BEV tail: rows gathered back from the dense gradient at the active sites
+__global__ void __launch_bounds__(256)
+    from_dense_kernel(const float *__restrict__ dense, const int *__restrict__ indices, int n,
+                      const int *__restrict__ n_dev, int c, Grid g, int bev_layout, float *__restrict__ feats) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
+  if (t >= (long long)n * c) return;
+  const int i = (int)(t / c), ch = (int)(t % c);
+  const int4 q = __ldg(reinterpret_cast<const int4 *>(indices) + i);
+  size_t src;
+  if (bev_layout) src = (((size_t)q.x * c * g.z + (size_t)ch * g.z + q.w) * g.x + q.y) * g.y + q.z;
+  else src = ((size_t)q.x * c + ch) * ((size_t)g.x * g.y * g.z) + ((size_t)q.y * g.y + q.z) * g.z + q.w;
+  feats[t] = __ldg(dense + src);
+}
+
 // BEVFusionSparseEncoder tail (sparse_encoder.py:147-151): dense() [N,C,X,Y,Z] -> permute(0,1,4,2,3) ->
 // view(N, C*Z, X, Y), fused: bev[b, ch*Z + z, x, y].  A CTA takes 32 consecutive sites: their feature rows are read
 // coalesced into shared memory, then each warp writes one channel at a time for the 32 sites -- with sites in
@@ -481,6 +496,19 @@ BEVF_API int bevf_sparse_to_dense(const float *feats, const int *indices, int n,
     to_bev_kernel<<<blocks, 256, (size_t)32 * (c + 1) * sizeof(float), st>>>(feats, indices, n, n_dev, c, g, dense);
   }
   else to_dense_kernel<<<bevf::ceil_div(threads, 256), 256, 0, st>>>(feats, indices, n, n_dev, c, g, dense);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_dense_to_sparse(const float *dense, const int *indices, int n, const int *n_dev, int c, int batch,
+                                  const int *shape, int bev_layout, float *feats, void *stream) {
+  BEVF_CHECK_ARG(batch > 0 && c > 0 && n >= 0, "bad sizes");
+  if (n == 0) return BEVF_OK;
+  BEVF_CHECK_ARG(dense && indices && feats, "NULL tensor");
+  Grid g{batch, shape[0], shape[1], shape[2]};
+  const long long threads = (long long)n * c;
+  from_dense_kernel<<<bevf::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(dense, indices, n, n_dev, c, g,
+                                                                                   bev_layout, feats);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;
 }

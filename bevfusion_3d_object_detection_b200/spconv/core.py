@@ -61,6 +61,39 @@ class IndicePair:
                                                                                       dilation, subm)
 
 
+class _ToDense(torch.autograd.Function):
+    """dense() / dense_bev() through bevf_sparse_to_dense; backward gathers the dense gradient at the active sites
+    (bevf_dense_to_sparse), so the encoder trains through its BEV tail."""
+
+    @staticmethod
+    def forward(ctx, features, indices, batch_size, spatial_shape, bev_layout):
+        f = features.contiguous().float()
+        n, c = f.shape
+        X, Y, Z = spatial_shape
+        shape = (batch_size, c * Z, X, Y) if bev_layout else (batch_size, c, X, Y, Z)
+        out = torch.empty(shape, dtype=torch.float32, device=f.device)
+        with torch.cuda.device(f.device):
+            check(lib().bevf_sparse_to_dense(ptr(f), ptr(indices), int(n), None, int(c), batch_size,
+                                             i32_array(spatial_shape), ptr(out), int(bev_layout),
+                                             cur_stream(f.device)))
+        ctx.save_for_backward(indices)
+        ctx.meta = (n, c, batch_size, spatial_shape, bev_layout)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (indices,) = ctx.saved_tensors
+        n, c, batch_size, spatial_shape, bev_layout = ctx.meta
+        g = grad.contiguous().float()
+        out = torch.empty((n, c), dtype=torch.float32, device=g.device)
+        if n:
+            with torch.cuda.device(g.device):
+                check(lib().bevf_dense_to_sparse(ptr(g), ptr(indices), int(n), None, int(c), batch_size,
+                                                 i32_array(spatial_shape), int(bev_layout), ptr(out),
+                                                 cur_stream(g.device)))
+        return out, None, None, None, None
+
+
 class SparseConvTensor:
 
     def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None,
@@ -139,16 +172,7 @@ class SparseConvTensor:
 
     # ---- internals --------------------------------------------------------------------------------------
     def _to_dense(self, bev_layout):
-        f = self.features.contiguous().float()
-        n, c = f.shape
-        X, Y, Z = self.spatial_shape
-        shape = (self.batch_size, c * Z, X, Y) if bev_layout else (self.batch_size, c, X, Y, Z)
-        out = torch.empty(shape, dtype=torch.float32, device=f.device)
-        with torch.cuda.device(f.device):
-            check(lib().bevf_sparse_to_dense(ptr(f), ptr(self.indices), int(n), None, int(c), self.batch_size,
-                                             i32_array(self.spatial_shape), ptr(out), int(bev_layout),
-                                             cur_stream(f.device)))
-        return out
+        return _ToDense.apply(self.features, self.indices, self.batch_size, tuple(self.spatial_shape), bool(bev_layout))
 
     def coord_index(self):
         if self._index is None:

@@ -310,6 +310,10 @@ int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, const int *n
  * (sparse_encoder.py:147-151) dense().permute(0,1,4,2,3).view(B, C*Z, X, Y) (bev_layout != 0).  Fully written. */
 int bevf_sparse_to_dense(const float *feats, const int *indices, int n, const int *n_dev, int c, int batch,
                          const int *shape_host, float *dense, int bev_layout, void *stream);
+/* The transpose of bevf_sparse_to_dense (its backward in training): feats[i, :] = the dense tensor at site i, for
+ * either layout.  feats [n, c] is fully written for the first n (or *n_dev) rows. */
+int bevf_dense_to_sparse(const float *dense, const int *indices, int n, const int *n_dev, int c, int batch,
+                         const int *shape_host, int bev_layout, float *feats, void *stream);
 /* Rows re-ordered by perm (rank -> row, from bevf_spconv_index_build): out_indices[r] = indices[perm[r]]; features
  * copied as fp32 (out_f32 [n, c], optional) and / or as bf16 zero-padded to cin_pad columns (out_bf16, optional). */
 int bevf_spconv_permute_rows(const float *feats, const int *indices, const int *perm, int n, const int *n_dev, int c,
