@@ -46,7 +46,6 @@ __global__ void __launch_bounds__(kWThreads)
                             int kv, int cin, int cout, int rows_per_split, float *__restrict__ d_w) {
   __shared__ __align__(16) float Gs[WR][WT + 4];   // d_out rows   [r][co]
   __shared__ __align__(16) float Xs[WR][WT + 4];   // gathered in  [r][ci]
-  __shared__ int any_valid;
   const int n_out = n_out_dev ? min(*n_out_dev, ld) : n_out_host;
   const int k = blockIdx.y;
   const int cin_tiles = (cin + WT - 1) / WT;
@@ -65,38 +64,60 @@ __global__ void __launch_bounds__(kWThreads)
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   bool touched = false;
 
-  for (int j0 = j_begin; j0 < j_end; j0 += WR) {
-    const int j = j0 + lr;
-    int idx = -1;
-    if (j < j_end) idx = __ldg(pair_fwd + (size_t)k * ld + j);
-    if (tid == 0) any_valid = 0;
-    __syncthreads();
-    if (idx >= 0 && (tid & 15) == 0) any_valid = 1;
-    float g[4] = {0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (idx >= 0) {
+  // software pipeline: the rulebook entry of step s + 2 and the two row segments of step s + 1 are in flight while
+  // step s is multiplied (the entry -> row dependency would otherwise expose two global-memory latencies per 16 rows)
+  const int *pk = pair_fwd + (size_t)k * ld;
+  auto load_rows = [&](int idx, int j, float (&g)[4], float (&x)[4]) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (co0 + lc + c < cout) g[c] = __ldg(d_out + (size_t)j * cout + co0 + lc + c);
-        if (ci0 + lc + c < cin) x[c] = __ldg(feats + (size_t)idx * cin + ci0 + lc + c);
+    for (int c = 0; c < 4; ++c) { g[c] = 0.f; x[c] = 0.f; }
+    if (idx >= 0) {
+      const float *gp = d_out + (size_t)j * cout + co0 + lc;
+      const float *xp = feats + (size_t)idx * cin + ci0 + lc;
+      if (co0 + lc + 3 < cout && (cout & 3) == 0) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(gp));
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (co0 + lc + c < cout) g[c] = __ldg(gp + c);
+      }
+      if (ci0 + lc + 3 < cin && (cin & 3) == 0) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(xp));
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (ci0 + lc + c < cin) x[c] = __ldg(xp + c);
       }
     }
+  };
+  int idx_n = (j_begin + lr < j_end) ? __ldg(pk + j_begin + lr) : -1;
+  float g_n[4], x_n[4];
+  load_rows(idx_n, j_begin + lr, g_n, x_n);
+  int idx_nn = (j_begin + WR + lr < j_end) ? __ldg(pk + j_begin + WR + lr) : -1;
+
+  for (int j0 = j_begin; j0 < j_end; j0 += WR) {
+    const int idx_c = idx_n;
+    float g[4], x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { g[c] = g_n[c]; x[c] = x_n[c]; }
+    idx_n = idx_nn;
+    load_rows(idx_n, j0 + WR + lr, g_n, x_n);
+    idx_nn = (j0 + 2 * WR + lr < j_end) ? __ldg(pk + j0 + 2 * WR + lr) : -1;
+    // all threads are past the previous step's multiply here; skip steps whose 16 rows have no pair under this tap
+    if (!__syncthreads_or(idx_c >= 0)) continue;
+    touched = true;
     *reinterpret_cast<float4 *>(&Gs[lr][lc]) = make_float4(g[0], g[1], g[2], g[3]);
     *reinterpret_cast<float4 *>(&Xs[lr][lc]) = make_float4(x[0], x[1], x[2], x[3]);
     __syncthreads();
-    if (any_valid) {
-      touched = true;
 #pragma unroll
-      for (int r = 0; r < WR; ++r) {
-        const float4 gv = *reinterpret_cast<const float4 *>(&Gs[r][ty * 4]);
-        const float4 xv = *reinterpret_cast<const float4 *>(&Xs[r][tx * 4]);
-        const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
+    for (int r = 0; r < WR; ++r) {
+      const float4 gv = *reinterpret_cast<const float4 *>(&Gs[r][ty * 4]);
+      const float4 xv = *reinterpret_cast<const float4 *>(&Xs[r][tx * 4]);
+      const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], xa[b], acc[a][b]);
-      }
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ga[a], xa[b], acc[a][b]);
     }
-    __syncthreads();
   }
   if (!touched) return;
 #pragma unroll
