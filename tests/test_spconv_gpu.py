@@ -248,6 +248,9 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
     (32, 64, (3, 3, 3), 2, 1, 50000, (160, 160, 16)),
     (64, 128, (3, 3, 3), 2, (1, 1, 0), 30000, (128, 128, 11)),
     (128, 128, (1, 1, 3), (1, 1, 2), 0, 30000, (128, 128, 5)),     # conv_out: kv = 3
+    (16, 16, (1, 1, 1), 1, 0, 40000, (128, 128, 8)),               # kv = 1: a 3-tap item with one real tap
+    (32, 32, (2, 2, 2), 2, 0, 40000, (128, 128, 8)),               # kv = 8: the last item of the group has two taps
+    (64, 64, (3, 1, 1), 1, (1, 0, 0), 40000, (128, 128, 8)),       # kv = 3, unit stride regular conv
 ])
 def test_bf16_ts_kernel_strided_matches_ss_kernel(tc_variant, cin, cout, ksize, stride, padding, n, grid):
     """Strided (regular) sparse convs through the TS kernel: bit-identical to the SS kernel, which
@@ -270,7 +273,7 @@ def test_bf16_ts_kernel_strided_matches_ss_kernel(tc_variant, cin, cout, ksize, 
                                  precision="bf16", relu=True)
         torch.cuda.synchronize()
         outs.append(o.cpu().numpy())
-    assert datas.n_out > 20000 and np.abs(outs[0]).max() > 0
+    assert datas.n_out > 10000 and np.abs(outs[0]).max() > 0
     np.testing.assert_array_equal(outs[0], outs[1])
 
 
