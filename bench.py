@@ -514,7 +514,7 @@ def run_b200(args, rank, world, local_rank):
         print(f"[bench] table-build timing unavailable: {exc}", file=sys.stderr)
     # the dominant kernel family of the step
     if gemm_ms >= max(ms_vox, ms_pool):
-        roof = dict(kernel="spconv_ts_kernel x17 (operand in TMEM) + spconv_tc_kernel x4 (strided), aggregate", bound="tensor",
+        roof = dict(kernel="spconv_ts_kernel x21 (gathered operand in TMEM), aggregate", bound="tensor",
                     achieved=stages["sparse_encoder"]["gemm_tflops"], peak=pk["tc"], unit="TFLOP/s",
                     frac=stages["sparse_encoder"]["gemm_frac"], traffic=None)
     elif ms_pool >= ms_vox:
@@ -524,7 +524,7 @@ def run_b200(args, rank, world, local_rank):
         roof = dict(kernel="voxelize_mean (5 kernels)", bound="hbm", achieved=stages["voxelize_mean"]["gbs"],
                     peak=pk["hbm"], unit="GB/s", frac=stages["voxelize_mean"]["frac"], traffic=None)
     roof["peak_source"] = pk["src"]
-    tpath = os.path.join(ROOT, "profiles", "r1j_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1k_traffic.json")
     if roof["bound"] == "tensor" and os.path.exists(tpath):
         tr = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of the 21 launches (ncu --set full)
         roof["traffic"] = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / n_gemm
