@@ -230,6 +230,19 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
         outs.append((o.cpu().numpy(), ob.float().cpu().numpy()))
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    # bf16-only output with a bf16 skip connection (what the encoder's inner layers ask for): the TS kernel stages the
+    # tile in shared memory and writes it with TMA tensor stores
+    only = []
+    for variant in (0, 1):
+        tc_variant(variant)
+        o, ob = Fsp.implicit_gemm(t(feats), datas.pair_fwd, datas.n_out, packed, 27, c, c, precision="bf16",
+                                  bn_scale=t(scale), bn_shift=t(shift), residual=t(res).bfloat16(), relu=True,
+                                  want_bf16=True, want_f32=False)
+        torch.cuda.synchronize()
+        assert o is None
+        only.append(ob.float().cpu().numpy())
+    np.testing.assert_array_equal(only[0], only[1])
+    assert np.abs(only[1] - outs[1][1]).max() <= 2e-2 * max(1.0, np.abs(outs[1][1]).max())
     fq = torch.from_numpy(feats).bfloat16().float().numpy()
     wq = torch.from_numpy(w).bfloat16().float().numpy()
     # the scalar oracle on the first and last rows (all rows are covered by the bit-wise comparison above)
@@ -275,6 +288,15 @@ def test_bf16_ts_kernel_strided_matches_ss_kernel(tc_variant, cin, cout, ksize, 
         outs.append(o.cpu().numpy())
     assert datas.n_out > 10000 and np.abs(outs[0]).max() > 0
     np.testing.assert_array_equal(outs[0], outs[1])
+    only = []
+    for variant in (0, 1):   # bf16-only output: staged tile + TMA stores in the TS kernel
+        tc_variant(variant)
+        o, ob = Fsp.implicit_gemm(torch.from_numpy(feats).cuda(), datas.pair_fwd, datas.n_out, packed, kv, cin, cout,
+                                  precision="bf16", relu=True, want_bf16=True, want_f32=False)
+        torch.cuda.synchronize()
+        only.append(ob.float().cpu().numpy())
+    np.testing.assert_array_equal(only[0], only[1])
+    np.testing.assert_array_equal(only[1], torch.from_numpy(outs[1]).bfloat16().float().numpy())
 
 
 def test_fused_epilogue_matches_unfused(oracle_mod):
