@@ -441,6 +441,27 @@ def run_b200(args, rank, world, local_rank):
             timing="CUDA graph of %d calls each; not part of the timed frame step" % RING)
     except Exception as exc:
         print(f"[bench] depth-prep timing unavailable: {exc}", file=sys.stderr)
+    # ---- configs[4] (stress): the voxelizer on the 128-beam ~0.9 M-point sweep at 0.05 m voxels (2160 x 2160 x 41 grid),
+    #      where the five kernels are no longer launch-bound
+    try:
+        s_range = [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+        s_voxel = [0.05, 0.05, 0.2]
+        s_pts = torch.from_numpy(synthetic.stress_sweep(seed=0, point_range=s_range)).to(dev)
+        s_cap = 600000
+        s_f = torch.empty((s_cap, 5), device=dev)
+        s_c = torch.empty((s_cap, 4), dtype=torch.int32, device=dev)
+        s_s = torch.empty((s_cap,), dtype=torch.int32, device=dev)
+        s_num = _vl.voxelize_mean(s_pts, s_f, s_c, s_s, s_voxel, s_range, 10, s_cap)
+        torch.cuda.synchronize()
+        s_m = int(s_num.item())
+        ms_sv = graph_ms(lambda i: _vl.voxelize_mean(s_pts, s_f, s_c, s_s, s_voxel, s_range, 10, s_cap), 3)
+        by_sv = 4 * 5 * int(s_pts.shape[0]) + s_m * (4 * 5 + 16 + 4)
+        stages["voxelize_mean_stress"] = dict(ms=ms_sv, bytes=by_sv, gbs=by_sv / ms_sv / 1e6,
+                                              frac=by_sv / ms_sv / 1e6 / pk["hbm"], points=int(s_pts.shape[0]),
+                                              voxels=s_m, timing="CUDA graph of %d calls (inputs L2-warm)" % RING)
+        del s_pts, s_f, s_c, s_s
+    except Exception as exc:
+        print(f"[bench] stress voxelizer timing unavailable: {exc}", file=sys.stderr)
     # ---- configs[2] (training): forward + backward of the sparse encoder and of the fused bev_pool, one frame, eager
     try:
         from bevfusion_3d_object_detection_b200.sparse_encoder import NUSCENES_ENCODER_CFG, BEVFusionSparseEncoder
