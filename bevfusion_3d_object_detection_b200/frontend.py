@@ -130,10 +130,11 @@ class HostPipeline:
         self.e_done[slot].synchronize()
         return self.host[slot]
 
-    def submit_device(self, points, depth, ctx):
+    def submit_device(self, points, depth, ctx, ways=None):
         """Same rotation for inputs that already live on the device (no host copies): -> (slot, lidar, cam); the
-        returned maps are the plan's own buffers, valid until the slot comes round again."""
-        slot = self.n % self.depth
+        returned maps are the plan's own buffers, valid until the slot comes round again.  `ways` (<= depth) limits the
+        rotation to the first plans: without host copies to hide, two frames in flight keep the GPU busiest."""
+        slot = self.n % (min(ways, self.depth) if ways else self.depth)
         self.n += 1
         plan, compute = self.plans[slot], self.computes[slot]
         caller = torch.cuda.current_stream(self.device)
