@@ -545,7 +545,7 @@ def run_b200(args, rank, world, local_rank):
         roof = dict(kernel="voxelize_mean (5 kernels)", bound="hbm", achieved=stages["voxelize_mean"]["gbs"],
                     peak=pk["hbm"], unit="GB/s", frac=stages["voxelize_mean"]["frac"], traffic=None)
     roof["peak_source"] = pk["src"]
-    tpath = os.path.join(ROOT, "profiles", "r1k_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1l_traffic.json")
     if roof["bound"] == "tensor" and os.path.exists(tpath):
         tr = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of the 21 launches (ncu --set full)
         roof["traffic"] = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / n_gemm
