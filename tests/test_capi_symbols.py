@@ -55,3 +55,19 @@ def test_sass_is_sm100a_only():
     out = subprocess.run([cuobjdump, "-lelf", build.LIB], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_tensor_core_variant_knob_is_host_side():
+    """bevf_spconv_tc_variant only flips a process-wide setting (no CUDA call): query, set, restore."""
+    from bevfusion_3d_object_detection_b200 import _lib
+
+    L = _lib.lib()
+    cur = L.bevf_spconv_tc_variant(-1)
+    assert cur in (0, 1, 2)
+    assert L.bevf_spconv_tc_variant(0) == cur
+    assert L.bevf_spconv_tc_variant(-1) == 0
+    assert L.bevf_spconv_tc_variant(7) == 0          # out of range: ignored
+    assert L.bevf_spconv_tc_variant(cur) == 0
+    assert L.bevf_spconv_tc_variant(-1) == cur
+    assert L.bevf_spconv_tc_supported(64, 64) == 1 and L.bevf_spconv_tc_supported(5, 16) == 1
+    assert L.bevf_spconv_tc_supported(256, 64) == 0 and L.bevf_spconv_tc_cin_pad(5) == 16
