@@ -334,13 +334,13 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
     }
   }
   __syncthreads();
-  // line = (b*nz + z)*nx + x  ->  out[b, ch*nz + z, x, y]
+  // line = (b*nz + z)*nx + x  ->  out[b, z*C + ch, x, y]   (cat(unbind(dim=2), 1) of depth_lss.py:202: z-major channels)
   const int x_ = line % nx;
   const int bz = line / nx;
   const int z_ = bz % nz, b_ = bz / nz;
   for (int ch = warp; ch < C; ch += kFusedWarps) {
     if (lane < ycnt) {
-      size_t o = ((((size_t)b_ * C + ch) * nz + z_) * nx + x_) * (size_t)ny + y0 + lane;
+      size_t o = ((((size_t)b_ * nz + z_) * C + ch) * nx + x_) * (size_t)ny + y0 + lane;
       out[o] = tile[ch * (kTileY + 1) + lane];
     }
   }
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
   const int z_ = bz % nz, b_ = bz / nz;
   if (tile_starts && lo == t_end) {  // empty tile: nothing to transpose, just the zeros
     for (int ch = warp; ch < C; ch += kFusedWarps)
-      if (lane < ycnt) out[((((size_t)b_ * C + ch) * nz + z_) * nx + x_) * (size_t)ny + y0 + lane] = 0.f;
+      if (lane < ycnt) out[((((size_t)b_ * nz + z_) * C + ch) * nx + x_) * (size_t)ny + y0 + lane] = 0.f;
     return;
   }
   for (int i = threadIdx.x; i < C * (kTileY + 1); i += blockDim.x) tile[i] = 0.f;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32)
   __syncthreads();
   for (int ch = warp; ch < C; ch += kFusedWarps) {
     if (lane < ycnt) {
-      size_t o = ((((size_t)b_ * C + ch) * nz + z_) * nx + x_) * (size_t)ny + y0 + lane;
+      size_t o = ((((size_t)b_ * nz + z_) * C + ch) * nx + x_) * (size_t)ny + y0 + lane;
       out[o] = tile[ch * (kTileY + 1) + lane];
     }
   }
@@ -826,11 +826,10 @@ BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *c
   BEVF_CHECK_ARG(smem1 <= 200 * 1024, "pixel column does not fit in shared memory (%zu bytes)", smem1);
   if (c / 4 <= 32) {
     if (n_runs > 0) {
-      static bool configured = false;
-      if (!configured) {
+      static bevf::DeviceOnce configured;
+      if (configured.first()) {
         BEVF_CHECK_CUDA(cudaFuncSetAttribute(bev_pool_runs_phase1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              200 * 1024));
-        configured = true;
       }
       bev_pool_runs_phase1_kernel<1><<<n_cols * split, 256, smem1, st>>>(depth, ctx_nhwc, run_p0, run_len,
                                                                         col_run_starts, split, d, fh, fw, c, partial);
@@ -840,11 +839,10 @@ BEVF_API int bevf_bev_pool_fused_forward_runs(const float *depth, const float *c
         partial, cell_run_starts, cell_run_ids, interval_cell, tile_starts, n_int, c, nz, nx, ny, tiles_y, out);
   } else {
     if (n_runs > 0) {
-      static bool configured = false;
-      if (!configured) {
+      static bevf::DeviceOnce configured;
+      if (configured.first()) {
         BEVF_CHECK_CUDA(cudaFuncSetAttribute(bev_pool_runs_phase1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              200 * 1024));
-        configured = true;
       }
       bev_pool_runs_phase1_kernel<2><<<n_cols * split, 256, smem1, st>>>(depth, ctx_nhwc, run_p0, run_len,
                                                                         col_run_starts, split, d, fh, fw, c, partial);

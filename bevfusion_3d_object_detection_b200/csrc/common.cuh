@@ -36,6 +36,18 @@ struct Workspace {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Per-device "already configured" flag for function attributes (cudaFuncSetAttribute is per device / context, so a
+// process that drives several GPUs must set it on each).  One instance per call site: `static DeviceOnce once;`
+// then `if (once.first()) { ...set attributes... }`.  Thread-safe (atomic flags), at most 64 devices.
+struct DeviceOnce {
+  unsigned char done[64] = {0};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown device: always configure
+    return __atomic_exchange_n(&done[dev], (unsigned char)1, __ATOMIC_ACQ_REL) == 0;
+  }
+};
+
 }  // namespace bevf
 
 #define BEVF_CHECK_ARG(cond, ...)              \

@@ -310,7 +310,8 @@ class _BevPoolFused(torch.autograd.Function):
         d_ctx_nhwc = torch.empty_like(ctx_nhwc)
         with torch.cuda.device(dev):
             L = lib()
-            check(L.bevf_nchw_to_nhwc(ptr(out_grad), ptr(g_nhwc), t.B, int(c), t.nz * t.nx * t.ny, cur_stream(dev)))
+            # out[b, z*C + ch, x, y] (z-major channels, depth_lss.py:202) viewed as [B*nz, C, nx*ny] -> cell-major rows
+            check(L.bevf_nchw_to_nhwc(ptr(out_grad), ptr(g_nhwc), t.B * t.nz, int(c), t.nx * t.ny, cur_stream(dev)))
             check(L.bevf_bev_pool_fused_backward(ptr(g_nhwc), ptr(depth), ptr(ctx_nhwc), ptr(t.cell_of_point), int(bn),
                                                  int(d), int(fh), int(fw), int(c), ptr(d_depth), ptr(d_ctx_nhwc),
                                                  cur_stream(dev)))

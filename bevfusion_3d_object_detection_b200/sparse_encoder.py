@@ -8,7 +8,7 @@ from torch import nn
 
 from . import registry
 from .spconv import SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, SparseConv3d
-from .spconv.modules import _fold_bn, bn_is_foldable
+from .spconv.modules import _fold_bn, bn_is_foldable, wants_grad
 
 registry._LOCAL.setdefault("SubMConv3d", SubMConv3d)
 registry._LOCAL.setdefault("SparseConv3d", SparseConv3d)
@@ -49,7 +49,8 @@ class SparseBasicBlock(SparseModule):
         return getattr(self, self.norm2_name)
 
     def forward(self, x):
-        if self.downsample is None and bn_is_foldable(self.norm1) and bn_is_foldable(self.norm2):
+        if (self.downsample is None and bn_is_foldable(self.norm1) and bn_is_foldable(self.norm2)
+                and not wants_grad(x, self)):
             s1, b1 = _fold_bn(self.norm1)
             s2, b2 = _fold_bn(self.norm2)
             # the skip connection reads whichever copy of the block input exists (fp32, else the bf16 operand copy)

@@ -193,9 +193,15 @@ class SparseConvolution(SparseModule):
             input._features is not None and input._features.requires_grad))
         fused = bn_scale is not None or residual is not None or relu
         if needs_grad:
-            assert not fused, "fused BN/ReLU epilogues are inference-only"
             feats = _SparseConvFunction.apply(input.features, self.weight, self.bias, datas.pair_fwd, n_out,
                                               self._packed_weight(precision), precision)
+            if fused:   # the fused epilogues are inference-only: same arithmetic as explicit (differentiable) torch ops
+                if bn_scale is not None:
+                    feats = feats * bn_scale + bn_shift
+                if residual is not None:
+                    feats = feats + residual.to(feats.dtype)
+                if relu:
+                    feats = torch.relu(feats)
         else:
             kv = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
             use_bf16_in = precision == "bf16" and input._bf16 is not None

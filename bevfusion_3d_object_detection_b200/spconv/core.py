@@ -4,10 +4,14 @@ mmdet3d/models/layers, projects/SparseConvolution/sparse_conv.py:70-103,155-162)
 spatial_shape / batch_size / indice_dict / find_indice_pair / replace_feature / dense / shadow_copy.
 """
 import ctypes
+import os
 
 import torch
 
 from .._lib import check, cur_stream, i32_array, lib, ptr
+
+
+_CHECK_INDEX = os.environ.get("BEVFRONT_CHECK_INDEX", "0") == "1"
 
 
 class CoordIndex:
@@ -177,6 +181,11 @@ class SparseConvTensor:
     def coord_index(self):
         if self._index is None:
             self._index = CoordIndex(self.indices, self.batch_size, self.spatial_shape, sorted_rows=self._sorted_rows)
+            if _CHECK_INDEX:   # debug mode (one host sync per tensor): out-of-grid / duplicate coordinates raise here
+                code = self._index.error_code()
+                if code:
+                    raise ValueError("SparseConvTensor indices: " + ("a coordinate lies outside the grid" if code == 1
+                                                                    else "duplicate coordinates"))
         return self._index
 
     def __repr__(self):

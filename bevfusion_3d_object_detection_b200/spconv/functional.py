@@ -55,8 +55,8 @@ def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
                               (1, 1, 1), padding, dilation, True)
         out_shape = conv_out_shape(x.spatial_shape, ksize, stride, padding, dilation)
         reach = 1
-        for k, s in zip(ksize, stride):
-            reach *= min(k, -(-k // s))
+        for k, s, d in zip(ksize, stride, dilation):
+            reach *= min(k, -(-k // s)) if d == 1 else k   # gcd(dilation, stride) > 1: up to k outputs per axis
         cells = x.batch_size * out_shape[0] * out_shape[1] * out_shape[2]
         cap = max(1, min(n_in * reach, cells))
         out_bytes = int(L.bevf_spconv_index_bytes(x.batch_size, i32_array(out_shape)))

@@ -87,6 +87,18 @@ def bn_is_foldable(m):
             and m.running_mean is not None)
 
 
+def wants_grad(x, *modules):
+    """True when autograd will need a graph through `modules` applied to the sparse tensor `x` (model.eval() without
+    no_grad, frozen-BN fine-tuning, input gradients): the fused BN / ReLU / residual epilogues are inference-only, so
+    the callers then take the reference's unfused module sequence (spconv modules just run in that situation)."""
+    if not torch.is_grad_enabled():
+        return False
+    f = getattr(x, "_features", None)
+    if f is not None and f.requires_grad:
+        return True
+    return any(p.requires_grad for m in modules for p in m.parameters())
+
+
 class SparseSequential(SparseModule):
     """nn.Sequential that routes a SparseConvTensor: sparse modules receive the tensor, dense modules (BatchNorm1d,
     ReLU, ...) are applied to `.features`.  In eval mode a [conv, BatchNorm1d, ReLU] run is executed as ONE kernel
@@ -131,7 +143,7 @@ class SparseSequential(SparseModule):
             m = mods[i]
             if isinstance(m, SparseConvolution) and isinstance(input, SparseConvTensor) and m.fuse_epilogue:
                 bn = mods[i + 1] if i + 1 < len(mods) else None
-                if bn is not None and bn_is_foldable(bn):
+                if bn is not None and bn_is_foldable(bn) and not wants_grad(input, m, bn):
                     relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
                     scale, shift = _fold_bn(bn)
                     input = m(input, bn_scale=scale, bn_shift=shift, relu=relu)

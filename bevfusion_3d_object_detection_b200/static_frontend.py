@@ -126,8 +126,8 @@ class StaticFrontEnd:
                 cur = self.levels[lvl]
                 out_shape = Fsp.conv_out_shape(cur.shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
                 reach = 1
-                for k, s in zip(conv.kernel_size, conv.stride):
-                    reach *= min(k, -(-k // s))
+                for k, s, d in zip(conv.kernel_size, conv.stride, conv.dilation):
+                    reach *= min(k, -(-k // s)) if d == 1 else k   # gcd(dilation, stride) > 1: up to k outputs per axis
                 cells = self.batch * out_shape[0] * out_shape[1] * out_shape[2]
                 self.levels.append(_Level(min(cur.cap * reach, cells), out_shape, self.batch, self.dev))
                 lvl += 1
@@ -153,7 +153,7 @@ class StaticFrontEnd:
         self.slots = {}
         last_lvl = self.ops[-1]["level_out"]
         for lvl, c in chans.items():
-            cap = self.levels[lvl].cap
+            cap = self.levels[lvl].ld   # rows = the leading dimension the GEMM's TMA maps are encoded with (pad4(cap))
             need32 = (not bf16) or lvl == last_lvl or any(
                 op["conv"].need_f32 for op in self.ops if op["level_out"] == lvl)
             self.slots[lvl] = [dict(f32=torch.empty((cap, c), dtype=torch.float32, device=dev) if need32 else None,

@@ -190,7 +190,8 @@ def bev_pool_fused(depth, ctx, src, geom4, starts, lengths, B, nz, nx, ny):
     lib().oracle_bev_pool_fused(_p(depth, _f32p), _p(ctx, _f32p), _p(src, _i64p), _p(_i32(geom4), _i32p),
                                 _p(_i32(starts), _i32p), _p(_i32(lengths), _i32p), len(starts), BN, C, D, fH, fW,
                                 B, nz, nx, ny, _p(out, _f32p))
-    return out.reshape(B, C * nz, nx, ny)
+    # depth_lss.py:202 torch.cat(x.unbind(dim=2), 1): the collapsed channel index is z*C + ch (z-major)
+    return np.ascontiguousarray(out.transpose(0, 2, 1, 3, 4)).reshape(B, nz * C, nx, ny)
 
 
 def lidar_depth_image(points, laug_trans, laug_inv_rot, lidar2image, img_aug, H, W):

@@ -11,6 +11,14 @@ Two modules are produced:
   ref_voxel_fixed  the same sources with that ONE allocation changed to {gx,gy,gz} (applied with a text
                    substitution into a temporary directory outside the repo, so no reference source ever lands in the tree) so the reference
                    algorithm can run on the 1440x1440x41 nuScenes grid; this is the timed CPU voxelize arm.
+
+Since round 2 the reference's CUDA sources are built as well (for sm_100a, nvcc cross-compiles here without a GPU):
+  ref_bev_pool_cuda  bev_pool.cpp + bev_pool_cuda.cu, unmodified: bev_pool_forward / bev_pool_backward (K1 / K2)
+  ref_voxel_cuda     voxelization.cpp + voxelization_cuda.cu + scatter_points_cuda.cu (+ the two CPU files the
+                     dispatcher links), unmodified, -DWITH_CUDA: hard_voxelize (deterministic and not),
+                     dynamic_voxelize, dynamic_point_to_voxel_forward / _backward on the GPU
+They are the GPU-side oracle of the `-m gpu` tests (partial -1 rows of dynamic_voxelize, set equality of the
+non-deterministic voxelizer, dynamic scatter) and the same-box "kernel to beat" bench.py times next to ours.
 """
 import os
 import sys
@@ -57,6 +65,36 @@ def build(verbose=False):
              sources=[os.path.join(REF_SRC, "voxelization.cpp"), os.path.join(sd, "voxelization_cpu_fixed.cpp"),
                       os.path.join(REF_SRC, "scatter_points_cpu.cpp")],
              extra_include_paths=[REF_SRC], extra_cflags=["-O2"], build_directory=bd, verbose=verbose)
+    build_cuda(verbose)
+    return True
+
+
+_NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-D__CUDA_NO_HALF_OPERATORS__",
+               "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__", "--expt-relaxed-constexpr"]
+POOL_SRC = os.path.join(os.path.dirname(os.path.dirname(REF_SRC)), "bev_pool", "src")
+
+
+def build_cuda(verbose=False):
+    """The reference's CUDA ops for sm_100a (flags of projects/BEVFusion/setup.py:18-29 with the gencode list
+    replaced).  ~4 min the first time."""
+    if not os.path.isdir(REF_SRC):
+        return False
+    from torch.utils.cpp_extension import load
+
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")   # no GPU here: keep torch from guessing an arch list
+    if not built("ref_bev_pool_cuda"):
+        bd = os.path.join(OUT, "ref_bev_pool_cuda")
+        os.makedirs(bd, exist_ok=True)
+        load(name="ref_bev_pool_cuda", sources=[os.path.join(POOL_SRC, f) for f in ("bev_pool.cpp", "bev_pool_cuda.cu")],
+             extra_cflags=["-O2"], extra_cuda_cflags=_NVCC_FLAGS, build_directory=bd, verbose=verbose, with_cuda=True)
+    if not built("ref_voxel_cuda"):
+        bd = os.path.join(OUT, "ref_voxel_cuda")
+        os.makedirs(bd, exist_ok=True)
+        files = ["voxelization.cpp", "scatter_points_cpu.cpp", "scatter_points_cuda.cu", "voxelization_cpu.cpp",
+                 "voxelization_cuda.cu"]
+        load(name="ref_voxel_cuda", sources=[os.path.join(REF_SRC, f) for f in files],
+             extra_cflags=["-O2", "-DWITH_CUDA"], extra_cuda_cflags=_NVCC_FLAGS + ["-DWITH_CUDA"], build_directory=bd,
+             verbose=verbose, with_cuda=True)
     return True
 
 

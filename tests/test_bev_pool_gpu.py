@@ -108,8 +108,8 @@ def test_quick_cumsum_golden_on_gpu():
     np.testing.assert_allclose(out.cpu().numpy(), dense, rtol=1e-5, atol=1e-5)
 
 
-def _view_case(batch, n_cams, feature_size, image_size, D_bound, C, xb, seed):
-    vt = BaseViewTransform(8, C, image_size, feature_size, xb, xb, [-10.0, 10.0, 20.0], D_bound).cuda()
+def _view_case(batch, n_cams, feature_size, image_size, D_bound, C, xb, seed, zb=(-10.0, 10.0, 20.0)):
+    vt = BaseViewTransform(8, C, image_size, feature_size, xb, xb, list(zb), D_bound).cuda()
     rig = {k: torch.from_numpy(v).cuda() for k, v in synthetic.camera_rig(n_cams=n_cams, image_size=image_size,
                                                                          batch=batch).items()}
     geom = vt.get_geometry(**rig)
@@ -118,10 +118,13 @@ def _view_case(batch, n_cams, feature_size, image_size, D_bound, C, xb, seed):
     return vt, geom, depth, ctx
 
 
-@pytest.mark.parametrize("case", ["small_b2", "config_A", "config_C_custom", "stress_D236_b2"])
+@pytest.mark.parametrize("case", ["small_b2", "small_nz2_b2", "config_A", "config_C_custom", "stress_D236_b2"])
 def test_fused_forward_matches_reference_chain(oracle_mod, case):
     if case == "small_b2":
         vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 1)
+    elif case == "small_nz2_b2":     # two z slabs: the collapsed channel index must be z*C + ch (depth_lss.py:202)
+        vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 5,
+                                          zb=(-4.0, 6.0, 5.0))
     elif case == "config_C_custom":  # BASELINE configs[3]: 5 cams, 384x704 image, 48x88 features
         vt, geom, depth, ctx = _view_case(1, 5, (48, 88), (384, 704), [1.0, 60.0, 0.5], 80, [-54.0, 54.0, 0.3], 6)
     elif case == "stress_D236_b2":   # BASELINE configs[4]: 236 depth bins (dbound step 0.25), 2 frames per GPU
@@ -159,8 +162,10 @@ def test_fused_forward_matches_reference_chain(oracle_mod, case):
         assert tabs.use_runs and tabs.n_runs < 80_000   # ~N*D*fW runs of ~fH points
 
 
-def test_fused_backward_matches_autograd_of_reference_chain():
-    vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 2)
+@pytest.mark.parametrize("zb", [(-10.0, 10.0, 20.0), (-4.0, 6.0, 5.0)])
+def test_fused_backward_matches_autograd_of_reference_chain(zb):
+    vt, geom, depth, ctx = _view_case(2, 3, (8, 22), (64, 176), [1.0, 30.0, 1.0], 16, [-27.0, 27.0, 0.6], 2, zb=zb)
+    assert int(vt.nx[2]) == (1 if zb[2] == 20.0 else 2)
     B, N, D, fH, fW, _ = geom.shape
     C = ctx.shape[1]
     vt.build_tables(geom)

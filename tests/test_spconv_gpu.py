@@ -336,6 +336,38 @@ def test_fused_epilogue_matches_unfused(oracle_mod):
     np.testing.assert_allclose(out, un, rtol=1e-5, atol=1e-5)
 
 
+def test_eval_mode_with_grad_takes_unfused_path():
+    """model.eval() WITHOUT torch.no_grad() (frozen-BN fine-tuning, input gradients): the reference's spconv modules
+    just run; here the fused epilogues are inference-only, so the modules must fall back to the unfused sequence,
+    give the same values as the fused path and deliver gradients."""
+    from bevfusion_3d_object_detection_b200.sparse_encoder import make_sparse_convmodule
+
+    rng = np.random.default_rng(12)
+    shape, batch, c = [16, 14, 9], 1, 16
+    idx = random_sites(rng, 1500, batch, shape)
+    feats = rng.standard_normal((idx.shape[0], c)).astype(np.float32)
+    norm_cfg = dict(type="BN1d", eps=1e-3, momentum=0.01)
+    blk = SparseBasicBlock(c, c, norm_cfg=norm_cfg).cuda().eval()
+    seq = make_sparse_convmodule(c, c, 3, norm_cfg=norm_cfg, padding=1, indice_key="s", conv_type="SubMConv3d").cuda().eval()
+    with torch.no_grad():
+        want = seq(blk(tensor_from(idx, feats, shape, batch))).features.clone()
+    x = torch.from_numpy(feats).cuda().requires_grad_(True)
+    got = seq(blk(spconv.SparseConvTensor(x, torch.from_numpy(idx).cuda(), shape, batch))).features
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    got.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and float(x.grad.abs().max()) > 0
+    for p_ in list(blk.parameters()) + list(seq.parameters()):
+        assert p_.grad is not None and torch.isfinite(p_.grad).all()
+    # direct call of a conv with fused arguments under grad: explicit torch epilogue instead of an assertion
+    conv = blk.conv1
+    s_, b_ = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    xt = spconv.SparseConvTensor(x.detach().clone().requires_grad_(True), torch.from_numpy(idx).cuda(), shape, batch)
+    o = conv(xt, bn_scale=s_, bn_shift=b_, relu=True).features
+    with torch.no_grad():
+        o_ref = conv(tensor_from(idx, feats, shape, batch), bn_scale=s_, bn_shift=b_, relu=True).features
+    np.testing.assert_allclose(o.detach().cpu().numpy(), o_ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
 def _oracle_encoder(oracle_mod, enc, feats, idx, batch):
     """Walk the module tree of a BEVFusionSparseEncoder and redo every step with the oracle."""
     shape = list(enc.sparse_shape)
