@@ -4,6 +4,8 @@
   BEVFusionSparseEncoder                      projects/BEVFusion/bevfusion/sparse_encoder.py:13-156
 Module names (and therefore state-dict keys) follow the reference so its checkpoints load unchanged.
 """
+import os
+
 from torch import nn
 
 from . import registry
@@ -12,6 +14,14 @@ from .spconv.modules import _fold_bn, bn_is_foldable, wants_grad
 
 registry._LOCAL.setdefault("SubMConv3d", SubMConv3d)
 registry._LOCAL.setdefault("SparseConv3d", SparseConv3d)
+
+
+# bf16 path: keep the residual stream (block inputs / outputs) in fp32?  Measured at config A against the fp32 CPU
+# oracle chain (scripts/parity_config_a.py, profiles/README.md r2a): max error of the encoder output relative to its
+# scale 1.2e-2 with bf16 skip connections, 0.8e-2 with the fp32 stream -- both inside north_star's 2e-2 -- and the fp32
+# stream costs 13 % GEMM time (1.16 vs 1.02 ms: 9 layers write fp32 rows and lose the TMA-staged epilogue).  Default
+# off; env BEVFRONT_RESIDUAL_F32=1 or BEVFusionSparseEncoder.set_residual_f32(True) turns it on.
+RESIDUAL_F32_DEFAULT = os.environ.get("BEVFRONT_RESIDUAL_F32", "0") == "1"
 
 
 def replace_feature(out, new_features):
@@ -157,11 +167,28 @@ class BEVFusionSparseEncoder(SparseEncoder):
         self.conv_out = make_sparse_convmodule(encoder_out_channels, self.output_channels, kernel_size=(1, 1, 3),
                                                stride=(1, 1, 2), norm_cfg=norm_cfg, padding=0,
                                                indice_key="spconv_down2", conv_type="SparseConv3d")
-        # on the tensor-core path only the last conv's fp32 output is consumed (by dense()); the inner layers hand
-        # their bf16 operand copy to the next conv and to the skip connections
+        self.set_residual_f32(RESIDUAL_F32_DEFAULT)
+
+    def set_residual_f32(self, flag):
+        """Which layers of the tensor-core (bf16) path also write an fp32 copy of their output.  Always: the last conv
+        (dense() consumes it).  flag=True: additionally every layer whose output is a SparseBasicBlock's input -- the
+        residual stream (conv_input, the second conv of every block, the strided convs) -- so the skip connections add
+        in fp32 and bf16 rounding does not compound along the 8 residual blocks; the convolution operands stay bf16.
+        flag=False: inner layers hand only their bf16 operand copy on (fastest; skip connections read bf16)."""
+        self.residual_f32 = bool(flag)
         for m in self.modules():
-            if hasattr(m, "need_f32") and m is not self.conv_out[0]:
-                m.need_f32 = False
+            if hasattr(m, "need_f32") and hasattr(m, "indice_key"):
+                m.need_f32 = m is self.conv_out[0]
+        if not self.residual_f32:
+            return
+        feeds_block = None      # the conv whose output the next module reads
+        for m in [self.conv_input] + [blk for stage in self.encoder_layers for blk in stage]:
+            if isinstance(m, SparseBasicBlock):
+                if feeds_block is not None:
+                    feeds_block.need_f32 = True
+                feeds_block = m.conv2
+            else:
+                feeds_block = m[0]
 
     def forward(self, voxel_features, coors, batch_size):
         """voxel_features [M, C] fp32, coors [M, 4] (batch, x, y, z) -> [B, C_out * Z_out, X_out, Y_out]."""

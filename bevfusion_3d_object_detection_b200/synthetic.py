@@ -121,3 +121,25 @@ def camera_matrices(rig, lidar_yaw=0.0, lidar_scale=1.0, lidar_trans=(0.0, 0.0, 
     laug[:, :3, :3] = _rot_z(lidar_yaw) * lidar_scale
     laug[:, :3, 3] = np.asarray(lidar_trans, np.float64)
     return l2i.astype(np.float32), aug.astype(np.float32), laug.astype(np.float32)
+
+
+def init_encoder_weights(enc, seed=0):
+    """Seeded weights for a BEVFusionSparseEncoder-shaped module (there are no checkpoints offline): conv kernels
+    ~ N(0, 2 / (kv * Cin)) so that activations keep O(1) magnitude through the 21 layers (torch's default
+    kaiming_uniform(a=sqrt(5)) shrinks them by ~3x per layer and the output would measure nothing), BatchNorm1d
+    affine parameters and running statistics away from the identity so that the folded epilogues are exercised."""
+    import torch
+    from torch import nn
+
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in enc.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            elif hasattr(m, "indice_key") and hasattr(m, "weight"):
+                fan = m.weight.shape[-1] * (m.weight.numel() // (m.weight.shape[0] * m.weight.shape[-1]))
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan) ** 0.5)
+    return enc
