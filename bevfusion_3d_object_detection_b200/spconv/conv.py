@@ -13,6 +13,12 @@ from . import functional as Fsp
 from .core import SparseConvTensor
 from .modules import SparseModule
 
+def lib_cin_pad(c):
+    from .._lib import lib
+
+    return int(lib().bevf_spconv_tc_cin_pad(int(c)))
+
+
 _DEFAULT_PRECISION = os.environ.get("BEVFRONT_SPCONV_PRECISION", "fp32")
 
 
@@ -51,6 +57,11 @@ class _SparseConvFunction(torch.autograd.Function):
         n_in, n_out = features.shape[0], ctx.n_out
         grad_out = grad_out.contiguous().float()
         g_feat = g_w = None
+        bf16 = ctx.precision == "bf16" and n_in > 0 and n_out > 0
+        tc = bf16 and Fsp.tc_supported(cout, cin)       # data gradient = a (Cout -> Cin) convolution
+        tc_w = bf16 and Fsp.tc_supported(cin, cout)     # weight gradient: same channel pair as the forward
+        # bf16 operand copy of the output gradient, shared by the data and the weight gradient
+        g_bf16 = Fsp.cast_features_bf16(grad_out, lib_cin_pad(cout)) if (tc or tc_w) else None
         if ctx.needs_input_grad[0]:
             if n_in == 0 or n_out == 0:
                 g_feat = torch.zeros_like(features)
@@ -58,12 +69,16 @@ class _SparseConvFunction(torch.autograd.Function):
                 # W^T per tap in the parameter layout of a (Cout -> Cin) convolution: [Cin, kD, kH, kW, Cout]
                 wt = weight.detach().reshape(cout, kv, cin).permute(2, 1, 0).contiguous().view(
                     cin, *weight.shape[1:-1], cout)
-                prec = ctx.precision if (ctx.precision == "fp32" or Fsp.tc_supported(cout, cin)) else "fp32"
-                packed_t = Fsp.pack_weight_bf16(wt) if prec == "bf16" else Fsp.pack_weight_f32(wt)
+                packed_t = Fsp.pack_weight_bf16(wt) if tc else Fsp.pack_weight_f32(wt)
                 pb = Fsp.pair_bwd(pair_fwd, n_out, n_in)
-                g_feat, _ = Fsp.implicit_gemm(grad_out, pb, n_in, packed_t, kv, cout, cin, precision=prec)
+                g_feat, _ = Fsp.implicit_gemm(None if tc else grad_out, pb, n_in, packed_t, kv, cout, cin,
+                                              precision="bf16" if tc else "fp32", features_bf16=g_bf16)
         if ctx.needs_input_grad[1]:
-            g_w = Fsp.wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
+            if tc_w:   # tcgen05, both operands MN-major (csrc/spconv_wgrad_tc.cu)
+                f_bf16 = Fsp.cast_features_bf16(features.detach(), lib_cin_pad(cin))
+                g_w = Fsp.wgrad_bf16(f_bf16, g_bf16, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
+            else:
+                g_w = Fsp.wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
         g_b = grad_out.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return g_feat, g_w, g_b, None, None, None, None
 

@@ -138,6 +138,20 @@ def wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout):
     return out
 
 
+def wgrad_bf16(features_bf16, grad_out_bf16, pair_fwd, n_out, kv, cin, cout):
+    """d_weight [Cout, kv, Cin] fp32 on the tensor cores: bf16 operands (features [n_in, cin_pad], grad_out
+    [n_out, Cout]), fp32 accumulation."""
+    assert features_bf16.dtype == torch.bfloat16 and grad_out_bf16.dtype == torch.bfloat16
+    dev = features_bf16.device
+    out = torch.empty((cout, kv, cin), dtype=torch.float32, device=dev)
+    ld = pair_fwd.stride(0) if pair_fwd.shape[1] > 0 else max(n_out, 1)
+    with torch.cuda.device(dev):
+        check(lib().bevf_spconv_wgrad_bf16(ptr(features_bf16), ptr(grad_out_bf16), ptr(pair_fwd), int(ld), int(n_out),
+                                           int(kv), int(cin), int(features_bf16.shape[1]), int(cout), ptr(out),
+                                           cur_stream(dev)))
+    return out
+
+
 def tc_supported(cin, cout):
     return bool(lib().bevf_spconv_tc_supported(int(cin), int(cout)))
 

@@ -346,6 +346,14 @@ int bevf_spconv_pair_bwd(const int *pair_fwd, int ld, int n_out, const int *n_ou
                          int n_in, void *stream);
 int bevf_spconv_wgrad_f32(const float *feats, const float *d_out, const int *pair_fwd, int ld, int n_out,
                           const int *n_out_dev, int kv, int cin, int cout, float *d_weight_okc, void *stream);
+/*
+ * Same weight gradient on the tensor cores (tcgen05.mma with both operands MN-major, fp32 accumulation in TMEM):
+ * feats bf16 [n_in, cin_pad] (zero padded, bevf_spconv_cast_bf16), d_out bf16 [n_out, cout]; cin_pad and cout in
+ * {16, 32, 64, 128}.  d_weight_okc fp32 [Cout, kv, Cin] is zeroed first and reduced over row ranges with fp32 atomics.
+ * What spconv's implicit-GEMM backward-weight kernels compute (projects/SparseConvolution/sparse_functional.py:287-314).
+ */
+int bevf_spconv_wgrad_bf16(const void *feats_bf16, const void *d_out_bf16, const int *pair_fwd, int ld, int n_out, int kv,
+                           int cin, int cin_pad, int cout, float *d_weight_okc, void *stream);
 
 /*
  * bf16 tensor-core path (tcgen05.mma, fp32 accumulation in TMEM): features bf16 [n_in, cin_pad] (cin_pad =

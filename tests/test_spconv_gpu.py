@@ -500,6 +500,13 @@ def test_training_backward_matches_dense_autograd():
     (5, 16, (3, 3, 3), True, 1, 1, 2000, "fp32"),
     (64, 64, (3, 3, 3), True, 1, 1, 2500, "bf16"),           # data gradient on the tcgen05 kernels
     (32, 64, (3, 3, 3), False, 2, 1, 3000, "bf16"),          # 64 -> 32 data gradient: SS kernel
+    (16, 16, (3, 3, 3), True, 1, 1, 5000, "bf16"),           # wgrad: 8 taps per tcgen05.mma (M = 8 x 16)
+    (5, 16, (3, 3, 3), True, 1, 1, 4000, "bf16"),            # conv_input: Cin 5 padded to 16
+    (16, 32, (3, 3, 3), False, 2, 1, 4000, "bf16"),
+    (32, 32, (3, 3, 3), True, 1, 1, 4000, "bf16"),           # 4 taps per MMA, 7 tap sets in 2 groups
+    (64, 128, (3, 3, 3), False, 2, (1, 1, 0), 3000, "bf16"),  # two 64-column slabs of d_out
+    (128, 128, (3, 3, 3), True, 1, 1, 2500, "bf16"),         # one tap per MMA (two 64-channel slabs), 7 tap groups
+    (128, 128, (1, 1, 3), False, (1, 1, 2), 0, 2000, "bf16"),  # conv_out: kv = 3
 ])
 def test_conv_backward_matches_oracle(oracle_mod, cin, cout, ksize, subm, stride, padding, n, precision):
     """Data and weight gradients through the C ABI (inverse rulebook + gather-GEMM with transposed weights; tiled
@@ -517,8 +524,17 @@ def test_conv_backward_matches_oracle(oracle_mod, cin, cout, ksize, subm, stride
     l1_f, l1_w = oracle_mod.spconv_backward(np.abs(feats), np.abs(w), o_pair, np.abs(g))
     got_f, got_w = x.grad.cpu().numpy(), conv.weight.grad.cpu().numpy()
     assert got_f.shape == d_feats.shape and got_w.shape == d_w.shape
-    # weight gradient is always fp32 (fp32 atomics across row ranges: order-of-summation noise only)
-    assert (np.abs(got_w - d_w) <= 1e-5 * np.abs(d_w) + 2e-6 * l1_w).all(), float(np.abs(got_w - d_w).max())
+    if precision == "fp32":
+        # fp32 weight gradient (fp32 atomics across row ranges: order-of-summation noise only)
+        assert (np.abs(got_w - d_w) <= 1e-5 * np.abs(d_w) + 2e-6 * l1_w).all(), float(np.abs(got_w - d_w).max())
+    else:
+        # tcgen05 weight gradient: bf16 operands, fp32 accumulation -> equal to the oracle fed the SAME rounded operands
+        # up to fp32 summation order; and within 2e-2 of the fp32 answer's scale
+        rb = lambda a: torch.from_numpy(a).bfloat16().float().numpy()  # noqa: E731
+        _, d_w_r = oracle_mod.spconv_backward(rb(feats), w, o_pair, rb(g))
+        _, l1_r = oracle_mod.spconv_backward(np.abs(rb(feats)), np.abs(w), o_pair, np.abs(rb(g)))
+        assert (np.abs(got_w - d_w_r) <= 1e-5 * np.abs(d_w_r) + 4e-6 * l1_r).all(), float(np.abs(got_w - d_w_r).max())
+        assert np.abs(got_w - d_w).max() <= RTOL_BF16 * np.abs(d_w).max()
     if precision == "fp32":
         assert (np.abs(got_f - d_feats) <= 1e-5 * np.abs(d_feats) + 1e-6 * l1_f).all(), float(np.abs(got_f - d_feats).max())
     else:
