@@ -39,7 +39,7 @@ class _SparseConvFunction(torch.autograd.Function):
     weight gradient a tiled fp32 outer-product reduction (csrc/spconv_bwd.cu); no host round trips."""
 
     @staticmethod
-    def forward(ctx, features, weight, bias, pair_fwd, n_out, packed, precision):
+    def forward(ctx, features, weight, bias, pair_fwd, n_out, packed, precision, datas=None):
         cout, cin = weight.shape[0], weight.shape[-1]
         kv = weight.numel() // (cout * cin)
         out, _ = Fsp.implicit_gemm(features, pair_fwd, n_out, packed, kv, cin, cout, precision=precision, bias=bias)
@@ -47,6 +47,7 @@ class _SparseConvFunction(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.precision = precision
         ctx.n_out = n_out
+        ctx.datas = datas     # the rulebook object: layers that share it share its inverse (built once per step)
         return out
 
     @staticmethod
@@ -70,17 +71,31 @@ class _SparseConvFunction(torch.autograd.Function):
                 wt = weight.detach().reshape(cout, kv, cin).permute(2, 1, 0).contiguous().view(
                     cin, *weight.shape[1:-1], cout)
                 packed_t = Fsp.pack_weight_bf16(wt) if tc else Fsp.pack_weight_f32(wt)
-                pb = Fsp.pair_bwd(pair_fwd, n_out, n_in)
+                pb = getattr(ctx.datas, "pair_bwd_cache", None) if ctx.datas is not None else None
+                if pb is None or pb.shape[1] != n_in:
+                    pb = Fsp.pair_bwd(pair_fwd, n_out, n_in)
+                    if ctx.datas is not None:
+                        ctx.datas.pair_bwd_cache = pb
                 g_feat, _ = Fsp.implicit_gemm(None if tc else grad_out, pb, n_in, packed_t, kv, cout, cin,
-                                              precision="bf16" if tc else "fp32", features_bf16=g_bf16)
+                                              precision="bf16" if tc else "fp32", features_bf16=g_bf16,
+                                              timing_tag="data_gradient")
         if ctx.needs_input_grad[1]:
+            timing = Fsp.GEMM_TIMING
+            if timing is not None:   # profiling pass: events around the launch, useful flops from the rulebook
+                pairs = int((pair_fwd[:, :n_out] >= 0).sum().item())
+                ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+                      2.0 * pairs * cin * cout, "weight_gradient"]
+                ev[0].record()
             if tc_w:   # tcgen05, both operands MN-major (csrc/spconv_wgrad_tc.cu)
                 f_bf16 = Fsp.cast_features_bf16(features.detach(), lib_cin_pad(cin))
                 g_w = Fsp.wgrad_bf16(f_bf16, g_bf16, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
             else:
                 g_w = Fsp.wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
+            if timing is not None:
+                ev[1].record()
+                timing.append(tuple(ev))
         g_b = grad_out.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return g_feat, g_w, g_b, None, None, None, None
+        return g_feat, g_w, g_b, None, None, None, None, None
 
 
 class SparseConvolution(SparseModule):
@@ -209,7 +224,7 @@ class SparseConvolution(SparseModule):
         fused = bn_scale is not None or residual is not None or relu
         if needs_grad:
             feats = _SparseConvFunction.apply(input.features, self.weight, self.bias, datas.pair_fwd, n_out,
-                                              self._packed_weight(precision), precision)
+                                              self._packed_weight(precision), precision, datas)
             if fused:   # the fused epilogues are inference-only: same arithmetic as explicit (differentiable) torch ops
                 if bn_scale is not None:
                     feats = feats * bn_scale + bn_shift

@@ -157,7 +157,8 @@ def tc_supported(cin, cout):
 
 
 def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, precision="fp32", bias=None, bn_scale=None,
-                  bn_shift=None, residual=None, relu=False, features_bf16=None, want_bf16=False, want_f32=True):
+                  bn_shift=None, residual=None, relu=False, features_bf16=None, want_bf16=False, want_f32=True,
+                  timing_tag="forward"):
     """out[n_out, Cout] fp32 (and optionally its bf16 copy) = epilogue(sum_k feats[pair_fwd[k]] @ W[k]).
     `residual` may be fp32 or (tensor-core path) bf16.  want_f32=False (tensor-core path only) skips the fp32 output."""
     dev = pair_fwd.device
@@ -179,7 +180,8 @@ def implicit_gemm(features, pair_fwd, n_out, weight_packed, kv, cin, cout, preci
     timing = GEMM_TIMING
     if timing is not None:
         pairs = int((pair_fwd[:, :n_out] >= 0).sum().item())
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), 2.0 * pairs * cin * cout)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), 2.0 * pairs * cin * cout,
+              timing_tag)
     with torch.cuda.device(dev):
         st = cur_stream(dev)
         if timing is not None:

@@ -47,8 +47,12 @@ class _Level:
 
 class StaticFrontEnd:
 
-    def __init__(self, model, tables, device, batch=1, max_points=400000):
+    def __init__(self, model, tables, device, batch=1, max_points=400000, level_growth=None):
+        """level_growth: None sizes every strided level for its worst case (each input site reaching prod(ceil(k/s))
+        outputs: 8x per level); a number caps the growth per level at that factor (real LiDAR frames grow < 2x) -- the
+        kernels clip at the capacity, so `check_capacity()` must be called on a representative frame."""
         assert not model.training, "the static plan folds BatchNorm: eval mode only"
+        self.level_growth = level_growth
         self.model, self.tables, self.dev = model, tables, torch.device(device)
         assert isinstance(tables, BevPoolTables) and tables.use_runs, "camera branch needs the run tables"
         self.batch, self.max_points = int(batch), int(max_points)
@@ -129,7 +133,9 @@ class StaticFrontEnd:
                 for k, s, d in zip(conv.kernel_size, conv.stride, conv.dilation):
                     reach *= min(k, -(-k // s)) if d == 1 else k   # gcd(dilation, stride) > 1: up to k outputs per axis
                 cells = self.batch * out_shape[0] * out_shape[1] * out_shape[2]
-                self.levels.append(_Level(min(cur.cap * reach, cells), out_shape, self.batch, self.dev))
+                if self.level_growth is not None:
+                    reach = min(float(reach), float(self.level_growth))
+                self.levels.append(_Level(min(int(cur.cap * reach), cells), out_shape, self.batch, self.dev))
                 lvl += 1
                 op["pair"] = torch.empty((conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2],
                                           self.levels[lvl].ld), dtype=torch.int32, device=self.dev)
@@ -390,6 +396,14 @@ class StaticFrontEnd:
             out.append(dict(cin=conv.in_channels, cout=conv.out_channels, subm=bool(conv.subm), ms=ms, rows=n,
                             flops=2.0 * pairs * conv.in_channels * conv.out_channels))
         return out
+
+    def check_capacity(self):
+        """Raise if the last frame overflowed a level's capacity (only possible with level_growth set): the site
+        kernels count every site and clip the rows they write, so n_dev > cap means truncated output."""
+        for i, (lv, n) in enumerate(zip(self.levels, self.counts())):
+            if n > lv.cap:
+                raise RuntimeError(f"static plan: level {i} has {n} active sites but capacity {lv.cap}; raise "
+                                   "level_growth (or pass None for worst-case sizing)")
 
     def counts(self):
         """Active sites per level (one host sync; diagnostics only)."""

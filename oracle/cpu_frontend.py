@@ -72,29 +72,32 @@ def cpu_sparse_conv(feats, idx, shape, weight, ksize, stride, padding, dilation,
     return out, out_idx, [int(v) for v in out_shape]
 
 
-def _bn(bn, x):
+def _bn(bn, x, train=False):
+    if train:   # batch statistics (train-mode BatchNorm1d); running statistics are not updated by the checker
+        return torch.nn.functional.batch_norm(x, None, None, bn["weight"], bn["bias"], True, 0.0, bn["eps"])
     return torch.nn.functional.batch_norm(x, bn["mean"], bn["var"], bn["weight"], bn["bias"], False, 0.0, bn["eps"])
 
 
-def cpu_sparse_encoder(layers, feats, idx, shape, batch):
-    """layers: the plan produced by `encoder_plan` (weights on CPU) -> dense BEV [B, C*Z, X, Y]."""
+def cpu_sparse_encoder(layers, feats, idx, shape, batch, train=False):
+    """layers: the plan produced by `encoder_plan` (weights on CPU) -> dense BEV [B, C*Z, X, Y].  train=True: batch-
+    statistics BatchNorm; every op is a differentiable torch op, so autograd gives the reference formulation's backward
+    (gather -> mm -> scatter-add per tap and their transposes: what mmcv's CPU indice_conv_backward does)."""
     f, i, shp = feats, idx, list(shape)
     for L in layers:
         if L["type"] == "convmodule":
             f, i, shp = cpu_sparse_conv(f, i, shp, L["weight"], L["ksize"], L["stride"], L["padding"], L["dilation"],
                                         L["subm"])
-            f = torch.relu(_bn(L["bn"], f))
+            f = torch.relu(_bn(L["bn"], f, train))
         else:  # basic block
             h, _, _ = cpu_sparse_conv(f, i, shp, L["w1"], (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True)
-            h = torch.relu(_bn(L["bn1"], h))
+            h = torch.relu(_bn(L["bn1"], h, train))
             h, _, _ = cpu_sparse_conv(h, i, shp, L["w2"], (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True)
-            f = torch.relu(_bn(L["bn2"], h) + f)
+            f = torch.relu(_bn(L["bn2"], h, train) + f)
     c = f.shape[1]
     X, Y, Z = shp
-    dense = torch.zeros((batch, c, X, Y, Z), dtype=torch.float32)
     it = torch.from_numpy(i).long()
-    dense[it[:, 0], :, it[:, 1], it[:, 2], it[:, 3]] = f
-    return dense.permute(0, 1, 4, 2, 3).contiguous().view(batch, c * Z, X, Y)
+    dense = torch.zeros((batch, X, Y, Z, c), dtype=torch.float32).index_put((it[:, 0], it[:, 1], it[:, 2], it[:, 3]), f)
+    return dense.permute(0, 4, 3, 1, 2).contiguous().view(batch, c * Z, X, Y)
 
 
 def encoder_plan(enc):

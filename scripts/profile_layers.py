@@ -29,7 +29,7 @@ with torch.no_grad():
         Fsp.GEMM_TIMING = []
         enc(feats, coords, 1)
         torch.cuda.synchronize()
-        cur = [(a.elapsed_time(b), fl) for a, b, fl in Fsp.GEMM_TIMING]
+        cur = [(ev[0].elapsed_time(ev[1]), ev[2]) for ev in Fsp.GEMM_TIMING]
         rows = cur if rows is None else [(min(r[0], c[0]), c[1]) for r, c in zip(rows, cur)]
     Fsp.GEMM_TIMING = None
 convs = [m for m in enc.modules() if hasattr(m, "indice_key") and hasattr(m, "kernel_size")]
