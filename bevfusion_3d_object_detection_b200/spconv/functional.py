@@ -100,7 +100,9 @@ def pack_weight_bf16(weight):
     L = lib()
     cin_pad = L.bevf_spconv_tc_cin_pad(int(cin))
     w = weight.detach().contiguous().float()
-    out = torch.empty((kv, cout * cin_pad), dtype=torch.bfloat16, device=w.device)
+    L.bevf_spconv_packed_weight_bytes.restype = ctypes.c_longlong
+    nbytes = int(L.bevf_spconv_packed_weight_bytes(int(kv), int(cin), int(cout)))
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)   # UMMA image [+ fragment-order image]
     with torch.cuda.device(w.device):
         check(L.bevf_spconv_pack_weight_bf16(ptr(w), ptr(out), int(kv), int(cin), int(cout), cur_stream(w.device)))
     return out

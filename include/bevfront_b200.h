@@ -365,16 +365,21 @@ int bevf_spconv_wgrad_bf16(const void *feats_bf16, const void *d_out_bf16, const
 int bevf_spconv_tc_cin_pad(int cin);
 int bevf_spconv_tc_supported(int cin, int cout);
 /* Which gather-GEMM kernel bevf_spconv_gemm_bf16 launches: 0 = operand tiles in shared memory ("SS" tcgen05.mma)
- * everywhere; 1 (default; 2 is a synonym) = operand rows in tensor memory ("TS" form, TMA-swizzled halo, global loads
- * where the row range does not fit) for the channel pairs it is instantiated for -- 16->16, 32->32, 64->64, 128->128,
- * 16->32, 32->64, 64->128 -- and the SS kernel for the rest.  Results are bit-identical between the variants (same
- * bf16 products, same fp32 accumulation order).  variant < 0 only queries.  Returns the previous setting;
- * process-wide (also env BEVFRONT_TC_TS at load time). */
+ * everywhere; 2 = operand rows in tensor memory ("TS" form, TMA-swizzled halo, global loads where the row range does not
+ * fit) for the channel pairs it is instantiated for -- 16->16, 32->32, 64->64, 128->128, 16->32, 32->64, 64->128 -- and
+ * the SS kernel for the rest; 0 and 2 are bit-identical (same bf16 products, same fp32 accumulation order).
+ * 1 (default) = like 2, but the narrow layers (cin_pad <= 32, cout <= 64: 8 % of the BEVFusion encoder's flops) run on
+ * the register-gather kernel (mma.sync fragments loaded straight from L2, spconv_rg.cu): same products, fp32 sums in a
+ * different order.  variant < 0 only queries.  Returns the previous setting; process-wide (also env BEVFRONT_TC_TS). */
 int bevf_spconv_tc_variant(int variant);
 int bevf_spconv_cast_bf16(const float *src, void *dst_bf16, int n, int cin, int cin_pad, const int *n_dev,
                           void *stream);
 int bevf_spconv_pack_weight_bf16(const float *weight_okc, void *weight_packed, int kv, int cin, int cout,
                                  void *stream);
+/* Bytes of the packed-weight buffer bevf_spconv_pack_weight_bf16 writes: the UMMA image (kv*cout*cin_pad bf16) and,
+ * for the narrow layers (cin_pad <= 32, cout <= 64) that run on the register-gather kernel, a second image of the same
+ * size in mma.sync fragment order behind it. */
+long long bevf_spconv_packed_weight_bytes(int kv, int cin, int cout);
 int bevf_spconv_gemm_bf16(const void *feats_bf16, int n_in, const void *weight_packed, const int *pair_fwd, int ld, int n_out,
                           const int *n_out_dev, int kv, int cin_pad, int cout, const float *bias,
                           const float *bn_scale, const float *bn_shift, const float *residual,

@@ -222,7 +222,7 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
     packed = Fsp.pack_weight_bf16(torch.from_numpy(w).cuda())
     t = lambda a: torch.from_numpy(a).cuda()
     outs = []
-    for variant in (0, 1):
+    for variant in (0, 2):
         tc_variant(variant)
         o, ob = Fsp.implicit_gemm(t(feats), datas.pair_fwd, datas.n_out, packed, 27, c, c, precision="bf16",
                                   bn_scale=t(scale), bn_shift=t(shift), residual=t(res), relu=True, want_bf16=True)
@@ -233,7 +233,7 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
     # bf16-only output with a bf16 skip connection (what the encoder's inner layers ask for): the TS kernel stages the
     # tile in shared memory and writes it with TMA tensor stores
     only = []
-    for variant in (0, 1):
+    for variant in (0, 2):
         tc_variant(variant)
         o, ob = Fsp.implicit_gemm(t(feats), datas.pair_fwd, datas.n_out, packed, 27, c, c, precision="bf16",
                                   bn_scale=t(scale), bn_shift=t(shift), residual=t(res).bfloat16(), relu=True,
@@ -254,6 +254,58 @@ def test_bf16_ts_kernel_matches_ss_kernel_and_oracle(oracle_mod, tc_variant, c, 
         ref = np.maximum(ref * scale + shift + res[sl], 0.0)
         err = np.abs(outs[1][0][sl] - ref)
         assert (err <= 1e-5 * np.abs(ref) + 4e-6 * (l1 * scale + np.abs(shift) + np.abs(res[sl]))).all(), float(err.max())
+
+
+@pytest.mark.parametrize("cin,cout,subm,stride,n,grid", [
+    (16, 16, True, 1, 70000, (192, 192, 16)),
+    (5, 16, True, 1, 50000, (192, 192, 16)),       # conv_input: Cin 5 zero-padded to 16
+    (32, 32, True, 1, 60000, (160, 160, 16)),
+    (16, 32, False, 2, 60000, (192, 192, 16)),
+    (32, 64, False, 2, 50000, (160, 160, 16)),     # one m16 tile per warp iteration
+    (32, 16, True, 1, 30000, (128, 128, 8)),       # data gradient of a 16 -> 32 layer
+])
+def test_bf16_register_gather_kernel_matches_tcgen05_kernel(oracle_mod, tc_variant, cin, cout, subm, stride, n, grid):
+    """Default variant 1: the narrow layers (Cin <= 32) run on the register-gather kernel (spconv_rg.cu: mma.sync
+    fragments loaded straight from L2).  Same bf16 products and fp32 accumulation as the tcgen05 kernels, different
+    summation order: equal up to fp32 rounding, with and without the fused epilogue, fp32 and bf16-only outputs; a row
+    slice is also checked against the scalar oracle fed the same rounded operands."""
+    rng = np.random.default_rng(cin * 3 + cout)
+    shape, batch = list(grid), 1
+    idx = random_sites(rng, n, batch, shape, sort=True)
+    feats = rng.standard_normal((idx.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    x = tensor_from(idx, feats, shape, batch)
+    datas = Fsp.get_indice_pairs(x, (3, 3, 3), (stride,) * 3, (1, 1, 1), (1, 1, 1), subm)
+    packed = Fsp.pack_weight_bf16(torch.from_numpy(w).cuda())
+    n_out = datas.n_out
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    res = rng.standard_normal((n_out, cout)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    outs = {}
+    for variant in (0, 1):
+        tc_variant(variant)
+        plain, _ = Fsp.implicit_gemm(t(feats), datas.pair_fwd, n_out, packed, 27, cin, cout, precision="bf16")
+        fused, fb = Fsp.implicit_gemm(t(feats), datas.pair_fwd, n_out, packed, 27, cin, cout, precision="bf16",
+                                      bn_scale=t(scale), bn_shift=t(shift), residual=t(res), relu=True, want_bf16=True)
+        _, only = Fsp.implicit_gemm(t(feats), datas.pair_fwd, n_out, packed, 27, cin, cout, precision="bf16",
+                                    bn_scale=t(scale), bn_shift=t(shift), residual=t(res).bfloat16(), relu=True,
+                                    want_bf16=True, want_f32=False)
+        torch.cuda.synchronize()
+        outs[variant] = [a.float().cpu().numpy() for a in (plain, fused, fb, only)]
+    fq = torch.from_numpy(feats).bfloat16().float().numpy()
+    wq = torch.from_numpy(w).bfloat16().float().numpy()
+    pair = datas.pair_fwd.cpu().numpy()[:, :n_out]
+    l1 = oracle_mod.spconv_gemm(np.abs(fq), np.abs(wq), pair)
+    assert np.abs(outs[0][0]).max() > 0
+    assert (np.abs(outs[1][0] - outs[0][0]) <= 1e-5 * np.abs(outs[0][0]) + 4e-6 * l1).all()
+    tol = 1e-5 * np.abs(outs[0][1]) + 4e-6 * (l1 * scale + np.abs(shift) + np.abs(res))
+    assert (np.abs(outs[1][1] - outs[0][1]) <= tol).all()
+    for q in (2, 3):   # bf16 copies: one ulp of bf16 where the fp32 values straddle a rounding boundary
+        assert (np.abs(outs[1][q] - outs[0][q]) <= 2 ** -7 * np.abs(outs[0][q]) + tol).all()
+    sl = slice(0, min(4000, n_out))
+    ref = oracle_mod.spconv_gemm(fq, wq, np.ascontiguousarray(pair[:, sl]))
+    assert (np.abs(outs[1][0][sl] - ref) <= 1e-5 * np.abs(ref) + 4e-6 * l1[sl]).all()
 
 
 @pytest.mark.parametrize("cin,cout,ksize,stride,padding,n,grid", [
@@ -280,7 +332,7 @@ def test_bf16_ts_kernel_strided_matches_ss_kernel(tc_variant, cin, cout, ksize, 
     datas = Fsp.get_indice_pairs(x, ksize, st3, pd3, (1, 1, 1), False)
     packed = Fsp.pack_weight_bf16(torch.from_numpy(w).cuda())
     outs = []
-    for variant in (0, 1):
+    for variant in (0, 2):
         tc_variant(variant)
         o, _ = Fsp.implicit_gemm(torch.from_numpy(feats).cuda(), datas.pair_fwd, datas.n_out, packed, kv, cin, cout,
                                  precision="bf16", relu=True)
@@ -289,7 +341,7 @@ def test_bf16_ts_kernel_strided_matches_ss_kernel(tc_variant, cin, cout, ksize, 
     assert datas.n_out > 10000 and np.abs(outs[0]).max() > 0
     np.testing.assert_array_equal(outs[0], outs[1])
     only = []
-    for variant in (0, 1):   # bf16-only output: staged tile + TMA stores in the TS kernel
+    for variant in (0, 2):   # bf16-only output: staged tile + TMA stores in the TS kernel
         tc_variant(variant)
         o, ob = Fsp.implicit_gemm(torch.from_numpy(feats).cuda(), datas.pair_fwd, datas.n_out, packed, kv, cin, cout,
                                   precision="bf16", relu=True, want_bf16=True, want_f32=False)
