@@ -142,4 +142,112 @@ int rank_build(const unsigned *bitmap, long long nwords, int *word_prefix, int *
   return BEVF_OK;
 }
 
+// ---- one-launch form -------------------------------------------------------------------------------------------------
+// The bitmap is cut into <= kRankMaxChunks contiguous chunks (about two per SM).  A CTA takes the next chunk from an atomic
+// ticket (so every predecessor of a running chunk is itself running or done: the waits below cannot deadlock), counts
+// its set bits, publishes the count, sums its predecessors' counts (<= 591 flags, read 256 at a time), and scans its
+// chunk a second time -- from L2 -- writing word_prefix and emitting.  One launch instead of three and no per-tile
+// partials; `sync` = 1 + kRankMaxChunks ints, zeroed by the caller before the launch.
+constexpr int kRankMaxChunks = 592;
+
+template <typename Emit>
+__global__ void __launch_bounds__(kRankThreads)
+    rank_chunk_scan_kernel(const unsigned *__restrict__ bitmap, long long nwords, long long chunk_words, int nchunks,
+                           int *__restrict__ sync, int *__restrict__ word_prefix, int *__restrict__ total, Emit emit) {
+  __shared__ int ws[kRankThreads / 32];
+  __shared__ int s_tile, s_val;
+  int *counter = sync, *status = sync + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= nchunks) return;
+  const long long w0 = (long long)tile * chunk_words;
+  const long long w1 = w0 + chunk_words < nwords ? w0 + chunk_words : nwords;
+  auto block_sum = [&](int v) {   // every thread gets the CTA-wide sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) ws[warp] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kRankThreads / 32; ++w) t += ws[w];
+    return t;
+  };
+  int cnt = 0;
+  for (long long w = w0 + tid; w < w1; w += kRankThreads) cnt += __popc(__ldg(bitmap + w));
+  const int agg = block_sum(cnt);
+  if (tid == 0) atomicExch(status + tile, agg + 1);   // 0 = not yet published
+  int before = 0;
+  for (int t = tid; t < tile; t += kRankThreads) {
+    int v;
+    do {
+      v = *reinterpret_cast<volatile int *>(status + t);
+    } while (v == 0);
+    before += v - 1;
+  }
+  int run_base = block_sum(before);
+  if (tile == nchunks - 1 && tid == 0) *total = run_base + agg;
+  for (long long tb = w0; tb < w1; tb += kRankTile) {
+    const long long base = tb + (long long)tid * kRankItems;
+    unsigned wv[kRankItems];
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < kRankItems; ++k) {
+      const long long w = base + k;
+      wv[k] = (w < w1) ? __ldg(bitmap + w) : 0u;
+      local += __popc(wv[k]);
+    }
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    __syncthreads();
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    int wpre = 0, ttot = 0;
+#pragma unroll
+    for (int w = 0; w < kRankThreads / 32; ++w) {
+      if (w < warp) wpre += ws[w];
+      ttot += ws[w];
+    }
+    int run = run_base + wpre + inc - local;
+#pragma unroll
+    for (int k = 0; k < kRankItems; ++k) {
+      const long long w = base + k;
+      if (w < w1) {
+        word_prefix[w] = run;
+        unsigned bits = wv[k];
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          emit(run, ((unsigned long long)w << 5) | (unsigned)b);
+          run += 1;
+        }
+      }
+    }
+    run_base += ttot;
+  }
+}
+
+// `sync` must hold 1 + kRankMaxChunks zeroed ints
+template <typename Emit>
+int rank_build_fused(const unsigned *bitmap, long long nwords, int *word_prefix, int *sync, int *total_dev, Emit emit,
+                     cudaStream_t st) {
+  long long nchunks = (nwords + kRankTile - 1) / kRankTile;
+  if (nchunks > kRankMaxChunks) nchunks = kRankMaxChunks;
+  if (nchunks < 1) nchunks = 1;
+  long long chunk_words = (nwords + nchunks - 1) / nchunks;
+  chunk_words = (chunk_words + kRankTile - 1) / kRankTile * kRankTile;
+  nchunks = (nwords + chunk_words - 1) / chunk_words;
+  if (nchunks < 1) nchunks = 1;
+  rank_chunk_scan_kernel<<<(int)nchunks, kRankThreads, 0, st>>>(bitmap, nwords, chunk_words, (int)nchunks, sync, word_prefix,
+                                                              total_dev, emit);
+  BEVF_CHECK_LAUNCH();
+  return BEVF_OK;
+}
+
 }  // namespace bevf

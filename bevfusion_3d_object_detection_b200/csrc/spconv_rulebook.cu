@@ -31,6 +31,7 @@ struct IndexView {
 
 struct ConvGeom {
   int k[3], s[3], p[3], d[3];
+  int sh[3];   // log2(s) when s is a power of two, else -1
 };
 
 __device__ __forceinline__ long long lin_cell(const Grid &g, int b, int x, int y, int z) {
@@ -51,6 +52,38 @@ __device__ __forceinline__ int index_lookup(const IndexView &ix, int b, int x, i
   if (!((bits >> bit) & 1u)) return -1;
   const int rank = __ldg(ix.word_prefix + (cell >> 5)) + __popc(bits & ((1u << bit) - 1u));
   return ix.perm ? __ldg(ix.perm + rank) : rank;
+}
+
+// The k[2] taps of one (kx, ky) column are z-neighbours, i.e. (z is the fastest axis) cells of ONE bitmap word most of
+// the time: the word and its prefix are loaded once per column, not once per tap.  out[kz] = row or -1.
+template <typename IT>
+__device__ __forceinline__ void index_lookup_zcol(const IndexView &ix, int b, int x, int y, int z0, int dz, int kz_n,
+                                                  int *__restrict__ dst, size_t dst_stride) {
+  const bool xy_ok = (unsigned)x < (unsigned)ix.g.x && (unsigned)y < (unsigned)ix.g.y;
+  const IT base = xy_ok ? lin_cell_t<IT>(ix.g, b, x, y, 0) : (IT)0;
+  IT cur_w = ~(IT)0;
+  unsigned bits = 0u;
+  int pref = -1;
+  for (int kz = 0; kz < kz_n; ++kz) {
+    const int z = z0 + kz * dz;
+    int row = -1;
+    if (xy_ok && (unsigned)z < (unsigned)ix.g.z) {
+      const IT cell = base + (IT)z;
+      const IT w = cell >> 5;
+      if (w != cur_w) {
+        cur_w = w;
+        bits = __ldg(ix.bitmap + w);
+        pref = -1;
+      }
+      const unsigned bit = (unsigned)(cell & 31);
+      if ((bits >> bit) & 1u) {
+        if (pref < 0) pref = __ldg(ix.word_prefix + w);
+        const int rank = pref + __popc(bits & ((1u << bit) - 1u));
+        row = ix.perm ? __ldg(ix.perm + rank) : rank;
+      }
+    }
+    dst[(size_t)kz * dst_stride] = row;
+  }
 }
 
 constexpr int kRbBlocks = bevf::kNumSMs * 16;  // grid-stride kernels: the grid never grows with the buffer capacity
@@ -75,6 +108,30 @@ __global__ void mark_sites_kernel(const int *__restrict__ indices, int n, const 
 
 struct EmitNothing {
   __device__ void operator()(int, unsigned long long) const {}
+};
+
+// output sites of a strided conv straight from the rank scan: site `rank` = cell `key` (ascending cell order)
+struct EmitSites {
+  int *out_indices;
+  int cap, gx, gy, gz;
+  __device__ void operator()(int rank, unsigned long long key) const {
+    if (rank >= cap) return;
+    unsigned long long k = key;
+    int4 o;
+    if (k < (1ull << 32)) {   // 32-bit divisions for every grid below 2^32 cells
+      unsigned k32 = (unsigned)k;
+      o.w = (int)(k32 % (unsigned)gz); k32 /= (unsigned)gz;
+      o.z = (int)(k32 % (unsigned)gy); k32 /= (unsigned)gy;
+      o.y = (int)(k32 % (unsigned)gx); k32 /= (unsigned)gx;
+      o.x = (int)k32;
+    } else {
+      o.w = (int)(k % (unsigned long long)gz); k /= (unsigned long long)gz;
+      o.z = (int)(k % (unsigned long long)gy); k /= (unsigned long long)gy;
+      o.y = (int)(k % (unsigned long long)gx); k /= (unsigned long long)gx;
+      o.x = (int)k;
+    }
+    reinterpret_cast<int4 *>(out_indices)[rank] = o;
+  }
 };
 
 __global__ void fill_perm_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, Grid g,
@@ -109,43 +166,122 @@ __global__ void __launch_bounds__(256)
     const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + j);
     const int x = c.y + (kx - cg.k[0] / 2) * cg.d[0];
     const int y = c.z + (ky - cg.k[1] / 2) * cg.d[1];
-    for (int kz = 0; kz < cg.k[2]; ++kz) {
-      const int z = c.w + (kz - cg.k[2] / 2) * cg.d[2];
-      const int tap = (int)col * cg.k[2] + kz;
-      pair_fwd[(size_t)tap * ld + j] = index_lookup<IT>(ix, c.x, x, y, z);
+    index_lookup_zcol<IT>(ix, c.x, x, y, c.w - (cg.k[2] / 2) * cg.d[2], cg.d[2], cg.k[2],
+                          pair_fwd + (size_t)((int)col * cg.k[2]) * ld + j, (size_t)ld);
+  }
+}
+
+// The hot geometry (every 3 x 3 x 3, dilation-1 layer of the encoder), SubM (S = 1, centred) and strided alike: blockIdx.y is
+// kx (no division to split the work item), a thread takes one site and its three ky columns; the z triple of a column
+// lies in one or two bitmap words that are loaded once; all address arithmetic is 32-bit adds from the site's own cell.
+// ix.perm must be null (rows in ascending cell order).  x0/y0/z0 = input coordinate of tap (0, 0, 0) for the site.
+template <bool SUBM>
+__global__ void __launch_bounds__(256)
+    rulebook_k3_kernel(const int *__restrict__ sites, int n_host, const int *__restrict__ n_dev, int n_cap, IndexView ix,
+                       ConvGeom cg, int ld, int *__restrict__ pair_fwd) {
+  int n = n_host;
+  if (n_dev) n = min(*n_dev, n_cap);
+  const int kx = blockIdx.y;
+  const unsigned gz = (unsigned)ix.g.z, gyz = (unsigned)ix.g.y * gz;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(sites) + j);
+    const int x = SUBM ? c.y + kx - 1 : c.y * cg.s[0] - cg.p[0] + kx;
+    const int y0 = SUBM ? c.z - 1 : c.z * cg.s[1] - cg.p[1];
+    const int z0 = SUBM ? c.w - 1 : c.w * cg.s[2] - cg.p[2];
+    const bool x_ok = (unsigned)x < (unsigned)ix.g.x;
+    const unsigned base_x = ((unsigned)c.x * (unsigned)ix.g.x + (unsigned)x) * gyz;
+    int *dst = pair_fwd + (size_t)(kx * 9) * ld + j;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = y0 + ky;
+      int r0 = -1, r1 = -1, r2 = -1;
+      if (x_ok && (unsigned)y < (unsigned)ix.g.y) {
+        const unsigned cell0 = base_x + (unsigned)y * gz + (unsigned)z0;   // may wrap when z0 < 0: only used if z valid
+        const bool v0 = (unsigned)z0 < gz, v1 = (unsigned)(z0 + 1) < gz, v2 = (unsigned)(z0 + 2) < gz;
+        const unsigned ca = v0 ? cell0 : (v1 ? cell0 + 1u : cell0 + 2u);   // first valid cell of the triple
+        const unsigned cb = v2 ? cell0 + 2u : (v1 ? cell0 + 1u : cell0);   // last valid cell
+        if (v0 | v1 | v2) {
+          const unsigned wa = ca >> 5, wb = cb >> 5;
+          const unsigned ba = __ldg(ix.bitmap + wa);
+          const unsigned bb = wb != wa ? __ldg(ix.bitmap + wb) : ba;
+          int pa = -1, pb = -1;
+          auto look = [&](unsigned cell) {
+            const unsigned w = cell >> 5, bit = cell & 31u;
+            const unsigned bits = w == wa ? ba : bb;
+            if (!((bits >> bit) & 1u)) return -1;
+            int &pref = w == wa ? pa : pb;
+            if (pref < 0) pref = __ldg(ix.word_prefix + w);
+            return pref + __popc(bits & ((1u << bit) - 1u));
+          };
+          if (v0) r0 = look(cell0);
+          if (v1) r1 = look(cell0 + 1u);
+          if (v2) r2 = look(cell0 + 2u);
+        }
+      }
+      dst[(size_t)(ky * 3 + 0) * ld] = r0;
+      dst[(size_t)(ky * 3 + 1) * ld] = r1;
+      dst[(size_t)(ky * 3 + 2) * ld] = r2;
     }
   }
 }
 
-// strided conv, pass 1: every input marks the output sites it reaches; one work item per (input, kx, ky)
-template <typename IT>
+// strided conv, pass 1: every input marks the output sites it reaches.  One thread per input site.  Per AXIS the taps
+// that land on an output ((c + p - k d) a non-negative multiple of s, inside the grid) are found first -- <= K candidates
+// per axis, with shifts instead of divisions for power-of-two strides (the 27 per-tap divisions were what this kernel
+// spent its time on) -- then the candidate products are walked; the z outputs of one (ox, oy) are neighbouring cells of
+// one bitmap word (two when the run crosses a word) and go out as ONE atomicOr, skipped when the bits are already set.
+template <typename IT, int KMAX>
 __global__ void __launch_bounds__(256)
     strided_mark_kernel(const int *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom cg, Grid og,
                         unsigned *__restrict__ out_bitmap) {
   if (n_dev) n = min(n, *n_dev);
-  const unsigned kxy = (unsigned)(cg.k[0] * cg.k[1]);
-  const unsigned total = (unsigned)n * kxy;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const unsigned col = t / (unsigned)n;
-    const int i = (int)(t - col * (unsigned)n);
-    const int kx = (int)(col / (unsigned)cg.k[1]), ky = (int)(col % (unsigned)cg.k[1]);
+  const int lim[3] = {og.x, og.y, og.z};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int4 c = __ldg(reinterpret_cast<const int4 *>(indices) + i);
-    int ox = c.y + cg.p[0] - kx * cg.d[0];
-    if (ox < 0 || ox % cg.s[0]) continue;
-    ox /= cg.s[0];
-    if (ox >= og.x) continue;
-    int oy = c.z + cg.p[1] - ky * cg.d[1];
-    if (oy < 0 || oy % cg.s[1]) continue;
-    oy /= cg.s[1];
-    if (oy >= og.y) continue;
-    for (int kz = 0; kz < cg.k[2]; ++kz) {
-      int oz = c.w + cg.p[2] - kz * cg.d[2];
-      if (oz < 0 || oz % cg.s[2]) continue;
-      oz /= cg.s[2];
-      if (oz >= og.z) continue;
-      const IT cell = lin_cell_t<IT>(og, c.x, ox, oy, oz);
-      const unsigned m = 1u << (unsigned)(cell & 31);
-      if (!(out_bitmap[cell >> 5] & m)) atomicOr(out_bitmap + (cell >> 5), m);
+    const int cc[3] = {c.y, c.z, c.w};
+    int cand[3][KMAX];   // output coordinate per tap, -1 = the tap lands on no output (constant indices: registers)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        int q = -1;
+        if (k < cg.k[a]) {
+          const int t = cc[a] + cg.p[a] - k * cg.d[a];
+          if (t >= 0) {
+            if (cg.sh[a] >= 0) {
+              if ((t & (cg.s[a] - 1)) == 0) q = t >> cg.sh[a];
+            } else if (t % cg.s[a] == 0) {
+              q = t / cg.s[a];
+            }
+            if (q >= lim[a]) q = -1;
+          }
+        }
+        cand[a][k] = q;
+      }
+    }
+#pragma unroll
+    for (int kx = 0; kx < KMAX; ++kx) {
+      if (cand[0][kx] < 0) continue;
+#pragma unroll
+      for (int ky = 0; ky < KMAX; ++ky) {
+        if (cand[1][ky] < 0) continue;
+        const IT base = lin_cell_t<IT>(og, c.x, cand[0][kx], cand[1][ky], 0);
+        IT cur_w = ~(IT)0;
+        unsigned mask = 0u;
+#pragma unroll
+        for (int kz = 0; kz < KMAX; ++kz) {
+          if (cand[2][kz] < 0) continue;
+          const IT cell = base + (IT)cand[2][kz];
+          const IT w = cell >> 5;
+          if (w != cur_w) {
+            if (mask && (out_bitmap[cur_w] & mask) != mask) atomicOr(out_bitmap + cur_w, mask);
+            cur_w = w;
+            mask = 0u;
+          }
+          mask |= 1u << (unsigned)(cell & 31);
+        }
+        if (mask && (out_bitmap[cur_w] & mask) != mask) atomicOr(out_bitmap + cur_w, mask);
+      }
     }
   }
 }
@@ -160,19 +296,26 @@ __global__ void __launch_bounds__(256)
     unsigned bits = __ldg(bitmap + w);
     if (!bits) continue;
     int rank = __ldg(word_prefix + w);
-    const IT base = (IT)w << 5;
+    // coordinates of the word's first cell (three divisions per word, not per site), then carried forward bit by bit
+    IT key = (IT)w << 5;
+    int z0 = (int)(key % (IT)og.z); key /= (IT)og.z;
+    int y0 = (int)(key % (IT)og.y); key /= (IT)og.y;
+    int x0 = (int)(key % (IT)og.x); key /= (IT)og.x;
+    int b0 = (int)key;
+    int last = 0;
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
-      if (rank < cap) {
-        IT key = base + (IT)b;
-        int4 o;
-        o.w = (int)(key % (IT)og.z); key /= (IT)og.z;
-        o.z = (int)(key % (IT)og.y); key /= (IT)og.y;
-        o.y = (int)(key % (IT)og.x); key /= (IT)og.x;
-        o.x = (int)key;
-        reinterpret_cast<int4 *>(out_indices)[rank] = o;
+      z0 += b - last;
+      last = b;
+      while (z0 >= og.z) {
+        z0 -= og.z;
+        if (++y0 >= og.y) {
+          y0 = 0;
+          if (++x0 >= og.x) { x0 = 0; ++b0; }
+        }
       }
+      if (rank < cap) reinterpret_cast<int4 *>(out_indices)[rank] = make_int4(b0, x0, y0, z0);
       rank += 1;
     }
   }
@@ -193,11 +336,8 @@ __global__ void __launch_bounds__(256)
     const int4 o = __ldg(reinterpret_cast<const int4 *>(out_indices) + j);
     const int x = o.y * cg.s[0] - cg.p[0] + kx * cg.d[0];
     const int y = o.z * cg.s[1] - cg.p[1] + ky * cg.d[1];
-    for (int kz = 0; kz < cg.k[2]; ++kz) {
-      const int z = o.w * cg.s[2] - cg.p[2] + kz * cg.d[2];
-      const int tap = (int)col * cg.k[2] + kz;
-      pair_fwd[(size_t)tap * ld + j] = index_lookup<IT>(ix, o.x, x, y, z);
-    }
+    index_lookup_zcol<IT>(ix, o.x, x, y, o.w * cg.s[2] - cg.p[2], cg.d[2], cg.k[2],
+                          pair_fwd + (size_t)((int)col * cg.k[2]) * ld + j, (size_t)ld);
   }
 }
 
@@ -275,6 +415,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+constexpr int kScalarInts = 64 + 1 + bevf::kRankMaxChunks + 7;
+
 struct IndexMem {
   unsigned *bitmap;
   int *word_prefix;
@@ -298,7 +440,7 @@ int grid_words(int batch, const int *shape, long long &nwords) {
 size_t carve_index(IndexMem &m, void *mem, size_t bytes, long long nwords) {
   bevf::Workspace a(mem, bytes);
   m.nwords = nwords;
-  m.scalars = a.take<int>(64);
+  m.scalars = a.take<int>(kScalarInts);   // [0] total, [1] error flag, [64 ..] ticket + chunk flags of the rank scan
   m.bitmap = a.take<unsigned>((size_t)nwords);
   m.word_prefix = a.take<int>((size_t)nwords);
   m.block_counts = a.take<int>((size_t)bevf::rank_num_blocks(nwords));
@@ -311,6 +453,9 @@ void fill_geom(ConvGeom &cg, const int *k, const int *s, const int *p, const int
     cg.s[j] = s ? s[j] : 1;
     cg.p[j] = p ? p[j] : 0;
     cg.d[j] = d ? d[j] : 1;
+    cg.sh[j] = -1;
+    for (int b = 0; b < 16; ++b)
+      if (cg.s[j] == (1 << b)) cg.sh[j] = b;
   }
 }
 
@@ -354,13 +499,13 @@ BEVF_API int bevf_spconv_index_build(const int *indices, int n, const int *n_dev
   BEVF_CHECK_ARG((reinterpret_cast<uintptr_t>(indices) & 15u) == 0, "indices must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   Grid g{batch, shape[0], shape[1], shape[2]};
-  BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
+  BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, kScalarInts * sizeof(int), st));
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
   if (n > 0) {
     mark_sites_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, n_dev, g, m.bitmap, m.scalars + 1);
     BEVF_CHECK_LAUNCH();
   }
-  rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitNothing{}, st);
+  rc = bevf::rank_build_fused(m.bitmap, nwords, m.word_prefix, m.scalars + 64, m.scalars, EmitNothing{}, st);
   if (rc) return rc;
   if (perm && n > 0) {
     fill_perm_kernel<<<bevf::ceil_div(n, 256), 256, 0, st>>>(indices, n, n_dev, g, m.bitmap, m.word_prefix, perm);
@@ -396,6 +541,14 @@ BEVF_API int bevf_spconv_subm_rulebook(const int *indices, int n, const int *n_d
   fill_geom(cg, ksize, nullptr, nullptr, dilation);
   const long long threads = (long long)n * ksize[0] * ksize[1];
   BEVF_CHECK_ARG(threads < (1ll << 32), "rulebook with %lld (site, tap column) items is not supported", threads);
+  const bool k3 = ksize[0] == 3 && ksize[1] == 3 && ksize[2] == 3 && (!dilation || (dilation[0] == 1 && dilation[1] == 1 &&
+                                                                                  dilation[2] == 1));
+  if (k3 && !perm && nwords < (1ll << 26)) {   // the encoder's SubM layers: specialised kernel, grid.y = kx
+    const int bx = bevf::ceil_div(n, 256) < kRbBlocks / 3 ? bevf::ceil_div(n, 256) : kRbBlocks / 3;
+    rulebook_k3_kernel<true><<<dim3(bx, 3), 256, 0, (cudaStream_t)stream>>>(indices, n, n_dev, n, ix, cg, ld, pair_fwd);
+    BEVF_CHECK_LAUNCH();
+    return BEVF_OK;
+  }
   const int blocks = (int)(bevf::ceil_div(threads, 256) < kRbBlocks ? bevf::ceil_div(threads, 256) : kRbBlocks);
   if (nwords < (1ll << 26))
     subm_rulebook_kernel<unsigned><<<blocks, 256, 0, (cudaStream_t)stream>>>(indices, n, n_dev, ix, cg, ld, pair_fwd);
@@ -427,24 +580,24 @@ BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, const in
   Grid og{batch, os[0], os[1], os[2]};
   ConvGeom cg;
   fill_geom(cg, ksize, stride, padding, dilation);
-  BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, 64 * sizeof(int), st));
+  BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, kScalarInts * sizeof(int), st));
   BEVF_CHECK_CUDA(cudaMemsetAsync(m.bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
   if (n_in > 0) {
-    const long long items = (long long)n_in * ksize[0] * ksize[1];
-    BEVF_CHECK_ARG(items < (1ll << 32), "%lld (site, tap column) items are not supported", items);
+    const long long items = (long long)n_in;
     const int blocks = (int)(bevf::ceil_div(items, 256) < kRbBlocks ? bevf::ceil_div(items, 256) : kRbBlocks);
-    if (nwords < (1ll << 26)) strided_mark_kernel<unsigned><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
-    else strided_mark_kernel<long long><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+    const bool small_k = ksize[0] <= 3 && ksize[1] <= 3 && ksize[2] <= 3;
+    if (nwords < (1ll << 26)) {
+      if (small_k) strided_mark_kernel<unsigned, 3><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+      else strided_mark_kernel<unsigned, 7><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+    } else {
+      if (small_k) strided_mark_kernel<long long, 3><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+      else strided_mark_kernel<long long, 7><<<blocks, 256, 0, st>>>(in_indices, n_in, n_in_dev, cg, og, m.bitmap);
+    }
     BEVF_CHECK_LAUNCH();
   }
-  rc = bevf::rank_build(m.bitmap, nwords, m.word_prefix, m.block_counts, m.scalars, EmitNothing{}, st);
+  rc = bevf::rank_build_fused(m.bitmap, nwords, m.word_prefix, m.scalars + 64, m.scalars,
+                              EmitSites{out_indices, cap, og.x, og.y, og.z}, st);
   if (rc) return rc;
-  {
-    const int blocks = (int)(bevf::ceil_div(nwords, 256) < kRbBlocks ? bevf::ceil_div(nwords, 256) : kRbBlocks);
-    if (nwords < (1ll << 26)) emit_sites_kernel<unsigned><<<blocks, 256, 0, st>>>(m.bitmap, m.word_prefix, nwords, og, out_indices, cap);
-    else emit_sites_kernel<long long><<<blocks, 256, 0, st>>>(m.bitmap, m.word_prefix, nwords, og, out_indices, cap);
-    BEVF_CHECK_LAUNCH();
-  }
   if (n_out_dev)
     BEVF_CHECK_CUDA(cudaMemcpyAsync(n_out_dev, m.scalars, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return BEVF_OK;
@@ -470,6 +623,15 @@ BEVF_API int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, con
   const long long threads = (long long)(n_out_dev ? ld : n_out) * ksize[0] * ksize[1];
   BEVF_CHECK_ARG(threads < (1ll << 32), "rulebook with %lld (site, tap column) items is not supported", threads);
   if (threads == 0) return BEVF_OK;
+  const bool k3 = ksize[0] == 3 && ksize[1] == 3 && ksize[2] == 3 && dilation[0] == 1 && dilation[1] == 1 && dilation[2] == 1;
+  if (k3 && !in_perm && nwords < (1ll << 26)) {
+    const int rows = n_out_dev ? ld : n_out;
+    const int bx = bevf::ceil_div(rows, 256) < kRbBlocks / 3 ? bevf::ceil_div(rows, 256) : kRbBlocks / 3;
+    rulebook_k3_kernel<false><<<dim3(bx, 3), 256, 0, (cudaStream_t)stream>>>(out_indices, n_out, n_out_dev, ld, ix, cg, ld,
+                                                                            pair_fwd);
+    BEVF_CHECK_LAUNCH();
+    return BEVF_OK;
+  }
   const int blocks = (int)(bevf::ceil_div(threads, 256) < kRbBlocks ? bevf::ceil_div(threads, 256) : kRbBlocks);
   if (nwords < (1ll << 26))
     strided_rulebook_kernel<unsigned><<<blocks, 256, 0, (cudaStream_t)stream>>>(out_indices, n_out_dev, n_out, ix, cg, ld,

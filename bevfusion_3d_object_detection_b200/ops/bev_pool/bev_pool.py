@@ -3,6 +3,8 @@
 (`BevPoolTables`, `bev_pool_fused`) in which depth x context, the kept / sort gathers, the interval sum,
 the permute and the collapse-Z of depth_lss.py:184-202, 723-725 are one kernel.
 """
+import os
+
 import torch
 
 from ..._lib import check, cur_stream, lib, ptr
@@ -205,6 +207,7 @@ class BevPoolTables:
         t.cell_of_point = cop
         t.B, t.nz, t.nx, t.ny = int(B), nzi, nxi, nyi
         t.run_p0, t.run_len, t.cell_run_ids = run_p0[:n_runs], run_len[:n_runs], run_ids[:n_runs]
+        t.run_pos = _inverse_permutation(t.cell_run_ids)
         t.col_run_starts, t.cell_run_starts, t.tile_starts = col_starts, crs[:n_int + 1], tile_starts
         t.use_runs = nk > 0 and n_runs * 4 <= nk
         return t
@@ -236,6 +239,7 @@ class BevPoolTables:
         self.col_run_starts = torch.cat([col.new_zeros(1), torch.cumsum(torch.bincount(col, minlength=n_cols), 0)]
                                         ).int().contiguous()
         self.cell_run_ids = by_cell.int().contiguous()
+        self.run_pos = _inverse_permutation(self.cell_run_ids)
         self.cell_run_starts = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)]).int().contiguous()
         self.use_runs = n_runs * 4 <= self.nk
         L = lib()
@@ -250,6 +254,17 @@ class BevPoolTables:
             t = torch.arange(n_tiles + 1)
             cell0 = (t // tiles_y) * self.ny + (t % tiles_y) * 32
             self.tile_starts = torch.searchsorted(self.interval_cell.long(), cell0).int()
+
+
+def _inverse_permutation(perm):
+    """run_pos[cell_run_ids[j]] = j: where a run's partial row goes so that every cell's rows are contiguous."""
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
+    return inv.contiguous()
+
+
+def fused_v2_supported(c, fw):
+    return fw % 4 == 0 and c % 16 == 0 and c <= 256
 
 
 def nchw_to_nhwc(x):
@@ -269,19 +284,31 @@ def nhwc_to_nchw(x):
     return out
 
 
+FUSED_V2 = os.environ.get("BEVFRONT_POOL_V2", "1") == "1"   # 0: the first-generation three-launch forward
+
+
 class _BevPoolFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, depth, ctx_feats, tables):
         # depth [BN, D, fH, fW], ctx_feats [BN, C, fH, fW] (NCHW, as the depthnet emits them)
         depth = depth.contiguous()
-        ctx_nhwc = nchw_to_nhwc(ctx_feats.contiguous())
+        ctx_feats = ctx_feats.contiguous()
         bn, d, fh, fw = depth.shape
         c = ctx_feats.shape[1]
         t = tables
         out = torch.empty((t.B, c * t.nz, t.nx, t.ny), dtype=torch.float32, device=depth.device)
+        v2 = t.use_runs and fused_v2_supported(c, fw) and FUSED_V2
+        ctx_nhwc = None if v2 else nchw_to_nhwc(ctx_feats)
         with torch.cuda.device(depth.device):
-            if t.use_runs:
+            if v2:   # two launches straight from the NCHW tensors (csrc/bev_pool_v2.cu)
+                partial = torch.empty((t.n_runs, c), dtype=torch.float32, device=depth.device)
+                check(lib().bevf_bev_pool_fused_forward_v2(
+                    ptr(depth), ptr(ctx_feats), ptr(t.run_p0), ptr(t.run_len), ptr(t.run_pos), t.n_runs,
+                    ptr(t.col_run_starts), ptr(t.cell_run_starts), ptr(t.interval_cell), ptr(t.tile_starts),
+                    t.n_intervals, int(bn), int(d), int(fh), int(fw), int(c), t.B, t.nz, t.nx, t.ny, ptr(partial),
+                    ptr(out), cur_stream(depth.device)))
+            elif t.use_runs:
                 partial = torch.empty((t.n_runs, c), dtype=torch.float32, device=depth.device)
                 check(lib().bevf_bev_pool_fused_forward_runs(
                     ptr(depth), ptr(ctx_nhwc), ptr(t.run_p0), ptr(t.run_len), t.n_runs, ptr(t.col_run_starts),
@@ -293,13 +320,16 @@ class _BevPoolFused(torch.autograd.Function):
                                                         ptr(t.interval_cell), t.n_intervals, t.nk, int(bn), int(d),
                                                         int(fh), int(fw), int(c), t.B, t.nz, t.nx, t.ny, ptr(out),
                                                         cur_stream(depth.device)))
-        ctx.save_for_backward(depth, ctx_nhwc)
+        ctx.save_for_backward(depth, ctx_feats if ctx_nhwc is None else ctx_nhwc)
+        ctx.ctx_is_nchw = ctx_nhwc is None
         ctx.tables = tables
         return out
 
     @staticmethod
     def backward(ctx, out_grad):
         depth, ctx_nhwc = ctx.saved_tensors
+        if ctx.ctx_is_nchw:   # the v2 forward read NCHW directly; the backward kernel wants channels-last
+            ctx_nhwc = nchw_to_nhwc(ctx_nhwc)
         t = ctx.tables
         bn, d, fh, fw = depth.shape
         c = ctx_nhwc.shape[3]

@@ -335,6 +335,17 @@ class StaticFrontEnd:
         t = self.tables
         bn, c, fh, fw = self.ctx.shape
         d = self.depth.shape[1]
+        import importlib
+
+        _bp = importlib.import_module(__package__ + ".ops.bev_pool.bev_pool")   # the module (the package re-exports a function of that name)
+
+        if _bp.FUSED_V2 and _bp.fused_v2_supported(int(c), int(fw)):
+            check(L.bevf_bev_pool_fused_forward_v2(ptr(self.depth), ptr(self.ctx), ptr(t.run_p0), ptr(t.run_len),
+                                                   ptr(t.run_pos), t.n_runs, ptr(t.col_run_starts), ptr(t.cell_run_starts),
+                                                   ptr(t.interval_cell), ptr(t.tile_starts), t.n_intervals, int(bn), int(d),
+                                                   int(fh), int(fw), int(c), t.B, t.nz, t.nx, t.ny, ptr(self.pool_partial),
+                                                   ptr(self.cam_bev), st))
+            return
         check(L.bevf_nchw_to_nhwc(ptr(self.ctx), ptr(self.ctx_nhwc), int(bn), int(c), int(fh * fw), st))
         check(L.bevf_bev_pool_fused_forward_runs(ptr(self.depth), ptr(self.ctx_nhwc), ptr(t.run_p0), ptr(t.run_len),
                                                  t.n_runs, ptr(t.col_run_starts), ptr(t.cell_run_starts),

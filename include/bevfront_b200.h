@@ -186,6 +186,17 @@ int bevf_bev_pool_fused_forward_runs(const float *depth, const float *ctx_nhwc, 
                                      const int *interval_cell, const int *tile_starts, int n_intervals, int bn, int d, int fh, int fw, int c,
                                      int b, int nz, int nx, int ny, float *partial, float *out, void *stream);
 /*
+ * Second-generation fused forward (csrc/bev_pool_v2.cu): same result, two launches, reads depth [BN, D, fH, fW] and the
+ * context features in their NATIVE NCHW layout [BN, C, fH, fW] (no channels-last pre-pass).  run_pos[q] = position of run
+ * q in cell order (the inverse permutation of cell_run_ids); `partial` [n_runs, C] fp32 scratch.  Needs fW % 4 == 0,
+ * C % 8 == 0, C <= 256 (BEVF_ERR_UNSUPPORTED otherwise: use the _runs form).  Replaces the data path of
+ * depth_lss.py:699-725 + :179-204 + bev_pool_cuda.cu:20-42.
+ */
+int bevf_bev_pool_fused_forward_v2(const float *depth, const float *ctx_nchw, const int *run_p0, const int *run_len,
+                                   const int *run_pos, int n_runs, const int *col_run_starts, const int *cell_run_starts,
+                                   const int *interval_cell, const int *tile_starts, int n_int, int bn, int d, int fh, int fw,
+                                   int c, int b, int nz, int nx, int ny, float *partial, float *out, void *stream);
+/*
  * Fused backward.  Given the output gradient in channels-last form out_grad_nhwc [B*nz*nx*ny, C]
  * (row = (b*nz+z)*nx*ny + x*ny + y; bevf_nchw_to_nhwc(out_grad, ., B, C, nz*nx*ny) produces it from
  * [B, C*nz, nx, ny]):

@@ -23,8 +23,12 @@ torch.cuda.synchronize()
 for lv, n in zip(plan.levels, plan.counts()):
     lv.hint = n
 torch.cuda.synchronize()
+from bevfusion_3d_object_detection_b200._lib import lib  # noqa: E402
+
 print("MARK")
+n0 = lib().bevf_launch_count()
 for _ in range(3):
     plan.run()
 torch.cuda.synchronize()
 print("counts", plan.counts())
+print("launches_per_frame", (lib().bevf_launch_count() - n0) // 3)

@@ -204,7 +204,7 @@ def test_linearity_and_zero_cells_full_size():
     np.testing.assert_allclose(float(out.double().sum()), float(total), rtol=1e-6)
 
 
-TABLE_FIELDS = ("src", "interval_starts", "interval_cell", "cell_of_point", "tile_starts", "run_p0", "run_len",
+TABLE_FIELDS = ("src", "interval_starts", "interval_cell", "cell_of_point", "tile_starts", "run_p0", "run_len", "run_pos",
                 "col_run_starts", "cell_run_ids", "cell_run_starts")
 
 
