@@ -69,6 +69,20 @@ class SparseBasicBlock(SparseModule):
             return self.conv2(out, bn_scale=s2, bn_shift=b2, residual=identity, relu=True)
         identity = x.features
         assert x.features.dim() == 2, f"x.features.dim()={x.features.dim()}"
+        from .spconv import bn_train
+
+        if self.downsample is None and bn_train.usable(self.norm1, identity) and bn_train.usable(self.norm2, identity):
+            # training: each conv is followed by ONE fused op (batch-statistics BN, ReLU, skip connection, bf16 copy)
+            bf16 = self.conv1._resolve_precision() == "bf16"
+            out = self.conv1(x)
+            y, yb = bn_train.bn_act_train(out.features, self.norm1, None, True, want_bf16=bf16)
+            out = replace_feature(out, y)
+            out._bf16 = yb
+            out = self.conv2(out)
+            y, yb = bn_train.bn_act_train(out.features, self.norm2, identity, True, want_bf16=bf16)
+            out = replace_feature(out, y)
+            out._bf16 = yb
+            return out
         out = self.conv1(x)
         out = replace_feature(out, self.norm1(out.features))
         out = replace_feature(out, self.relu(out.features))

@@ -39,10 +39,14 @@ class _SparseConvFunction(torch.autograd.Function):
     weight gradient a tiled fp32 outer-product reduction (csrc/spconv_bwd.cu); no host round trips."""
 
     @staticmethod
-    def forward(ctx, features, weight, bias, pair_fwd, n_out, packed, precision, datas=None):
+    def forward(ctx, features, weight, bias, pair_fwd, n_out, packed, precision, datas=None, features_bf16=None):
         cout, cin = weight.shape[0], weight.shape[-1]
         kv = weight.numel() // (cout * cin)
-        out, _ = Fsp.implicit_gemm(features, pair_fwd, n_out, packed, kv, cin, cout, precision=precision, bias=bias)
+        if precision != "bf16" or features_bf16 is None or features_bf16.shape[1] != lib_cin_pad(cin):
+            features_bf16 = None
+        out, _ = Fsp.implicit_gemm(features, pair_fwd, n_out, packed, kv, cin, cout, precision=precision, bias=bias,
+                                   features_bf16=features_bf16)
+        ctx.features_bf16 = features_bf16   # operand copy written by the producer (fused BN): reused by the weight gradient
         ctx.save_for_backward(features, weight, pair_fwd)
         ctx.has_bias = bias is not None
         ctx.precision = precision
@@ -62,7 +66,11 @@ class _SparseConvFunction(torch.autograd.Function):
         tc = bf16 and Fsp.tc_supported(cout, cin)       # data gradient = a (Cout -> Cin) convolution
         tc_w = bf16 and Fsp.tc_supported(cin, cout)     # weight gradient: same channel pair as the forward
         # bf16 operand copy of the output gradient, shared by the data and the weight gradient
-        g_bf16 = Fsp.cast_features_bf16(grad_out, lib_cin_pad(cout)) if (tc or tc_w) else None
+        g_bf16 = None
+        if tc or tc_w:
+            g_bf16 = getattr(grad_out, "_bevf_bf16", None)   # left by the fused BN backward: no cast pass
+            if g_bf16 is None or g_bf16.shape != (n_out, lib_cin_pad(cout)):
+                g_bf16 = Fsp.cast_features_bf16(grad_out, lib_cin_pad(cout))
         if ctx.needs_input_grad[0]:
             if n_in == 0 or n_out == 0:
                 g_feat = torch.zeros_like(features)
@@ -87,7 +95,9 @@ class _SparseConvFunction(torch.autograd.Function):
                       2.0 * pairs * cin * cout, "weight_gradient"]
                 ev[0].record()
             if tc_w:   # tcgen05, both operands MN-major (csrc/spconv_wgrad_tc.cu)
-                f_bf16 = Fsp.cast_features_bf16(features.detach(), lib_cin_pad(cin))
+                f_bf16 = ctx.features_bf16
+                if f_bf16 is None:
+                    f_bf16 = Fsp.cast_features_bf16(features.detach(), lib_cin_pad(cin))
                 g_w = Fsp.wgrad_bf16(f_bf16, g_bf16, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
             else:
                 g_w = Fsp.wgrad_f32(features, grad_out, pair_fwd, n_out, kv, cin, cout).view(weight.shape)
@@ -95,7 +105,7 @@ class _SparseConvFunction(torch.autograd.Function):
                 ev[1].record()
                 timing.append(tuple(ev))
         g_b = grad_out.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return g_feat, g_w, g_b, None, None, None, None, None
+        return g_feat, g_w, g_b, None, None, None, None, None, None
 
 
 class SparseConvolution(SparseModule):
@@ -224,7 +234,7 @@ class SparseConvolution(SparseModule):
         fused = bn_scale is not None or residual is not None or relu
         if needs_grad:
             feats = _SparseConvFunction.apply(input.features, self.weight, self.bias, datas.pair_fwd, n_out,
-                                              self._packed_weight(precision), precision, datas)
+                                              self._packed_weight(precision), precision, datas, input._bf16)
             if fused:   # the fused epilogues are inference-only: same arithmetic as explicit (differentiable) torch ops
                 if bn_scale is not None:
                     feats = feats * bn_scale + bn_shift

@@ -149,6 +149,24 @@ class SparseSequential(SparseModule):
                     input = m(input, bn_scale=scale, bn_shift=shift, relu=relu)
                     i += 3 if relu else 2
                     continue
+            if (isinstance(m, SparseConvolution) and isinstance(input, SparseConvTensor) and i + 1 < len(mods)
+                    and isinstance(mods[i + 1], nn.BatchNorm1d) and mods[i + 1].training):
+                # training: conv, then batch-statistics BatchNorm1d + ReLU as one fused op that also emits the bf16
+                # operand copy of the next conv (csrc/bn_train.cu)
+                from . import bn_train
+
+                out = m(input)
+                if bn_train.usable(mods[i + 1], out._features):
+                    relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                    y, yb = bn_train.bn_act_train(out._features, mods[i + 1], None, relu,
+                                                  want_bf16=m._resolve_precision() == "bf16")
+                    input = out.replace_feature(y)
+                    input._bf16 = yb
+                    i += 3 if relu else 2
+                    continue
+                input = out
+                i += 1
+                continue
             if is_spconv_module(m):
                 assert isinstance(input, SparseConvTensor)
                 input = m(input)

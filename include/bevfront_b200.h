@@ -396,6 +396,22 @@ int bevf_spconv_gemm_bf16(const void *feats_bf16, int n_in, const void *weight_p
                           const float *bn_scale, const float *bn_shift, const float *residual,
                           const void *residual_bf16, int relu, float *out_f32, void *out_bf16, void *stream);
 
+/*
+ * Train-mode BatchNorm1d over the n rows of a sparse tensor, fused with the ReLU / residual add around it and with the
+ * bf16 operand copy the next tensor-core conv reads (training split, BASELINE configs[2]).  Reference: the separate
+ * norm / relu / += identity ops of mmdet3d/models/layers/sparse_block.py:137-154 on torch.nn.BatchNorm1d (batch
+ * statistics, running statistics updated with `momentum`, unbiased running variance).
+ *   forward : y = relu?((x - mean) * invstd * gamma + beta [+ residual]); save_mean / save_invstd [c] for the backward;
+ *             y_bf16 optional.  sums_ws: 2*c doubles of scratch.  c % 4 == 0, c <= 256.
+ *   backward: dz = relu ? dy * (y > 0) : dy; dx (and optionally dx_bf16), d_residual = dz, dgamma, dbeta.
+ */
+int bevf_bn_train_forward(const float *x, const float *residual, const float *gamma, const float *beta, int n, int c,
+                          float eps, float momentum, int relu, float *running_mean, float *running_var, float *save_mean,
+                          float *save_invstd, double *sums_ws, float *y, void *y_bf16, void *stream);
+int bevf_bn_train_backward(const float *x, const float *dy, const float *y, const float *gamma, const float *save_mean,
+                           const float *save_invstd, int n, int c, int relu, double *sums_ws, float *dx, void *dx_bf16,
+                           float *d_residual, float *dgamma, float *dbeta, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -660,7 +660,8 @@ def _torch_conv(x, pair, w):
     return out
 
 
-def test_block_training_gradients_match_torch_autograd():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_block_training_gradients_match_torch_autograd(precision):
     """Train-mode stack: strided conv module (conv + BN + ReLU) -> SparseBasicBlock (conv, BN, ReLU, conv, BN, + skip,
     ReLU) -> dense BEV tail.  Output, input gradient and every parameter gradient against the same network written
     with torch gather / matmul autograd on the GPU rulebooks (the rulebooks are pinned bit-exact elsewhere)."""
@@ -681,11 +682,17 @@ def test_block_training_gradients_match_torch_autograd():
             if isinstance(m, nn.BatchNorm1d):
                 m.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, m.num_features).astype(np.float32)))
                 m.bias.copy_(torch.from_numpy((rng.standard_normal(m.num_features) * 0.1).astype(np.float32)))
-    spconv.set_default_precision("fp32")
-    x = torch.from_numpy(feats).cuda().requires_grad_(True)
-    t0 = spconv.SparseConvTensor(x, torch.from_numpy(idx).cuda(), shape, batch)
-    t1 = down(t0)
-    t2 = blk(t1)
+    spconv.set_default_precision(precision)
+    try:
+        x = torch.from_numpy(feats).cuda().requires_grad_(True)
+        t0 = spconv.SparseConvTensor(x, torch.from_numpy(idx).cuda(), shape, batch)
+        t1 = down(t0)
+        t2 = blk(t1)
+        from bevfusion_3d_object_detection_b200.spconv import bn_train
+        if bn_train.ENABLED:   # fused train-mode BN emitted the next operand copy
+            assert (t2._bf16 is not None) == (precision == "bf16")
+    finally:
+        spconv.set_default_precision("fp32")
     bev = t2.dense_bev()
     proj = torch.from_numpy(rng.standard_normal(tuple(bev.shape)).astype(np.float32)).cuda()
     (bev * proj).sum().backward()
@@ -707,15 +714,31 @@ def test_block_training_gradients_match_torch_autograd():
     y = torch.relu(bn(_torch_conv(h, p_subm, params["blk.conv1.weight"]), "blk.bn1"))
     y = bn(_torch_conv(y, p_subm, params["blk.conv2.weight"]), "blk.bn2")
     y = torch.relu(y + h)
-    np.testing.assert_allclose(t2.features.detach().cpu().numpy(), y.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    # fp32: order-of-summation noise only; bf16 tensor-core operands: 2e-2 of the scale per quantity
+    rt, at = (1e-4, 1e-4) if precision == "fp32" else (0.0, 2e-2 * float(y.detach().abs().max()))
+    np.testing.assert_allclose(t2.features.detach().cpu().numpy(), y.detach().cpu().numpy(), rtol=rt, atol=at)
     X, Y, Z = d_down.out_spatial_shape
     oi = d_down.out_indices[:d_down.n_out].long()
     dense = torch.zeros((batch, Z, X, Y, c1), device="cuda").index_put((oi[:, 0], oi[:, 3], oi[:, 1], oi[:, 2]), y)
     (dense.permute(0, 4, 1, 2, 3).reshape(batch, c1 * Z, X, Y) * proj).sum().backward()
     scale = float(xr.grad.abs().max())
-    np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-3, atol=1e-4 * scale)
     mine = dict(list(down.named_parameters(prefix="down")) + list(blk.named_parameters(prefix="blk")))
-    for name, ref in params.items():
-        sc = float(ref.grad.abs().max())
-        np.testing.assert_allclose(mine[name].grad.cpu().numpy(), ref.grad.cpu().numpy(), rtol=1e-3, atol=2e-4 * sc,
-                                   err_msg=name)
+    if precision == "fp32":
+        np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-3, atol=1e-4 * scale)
+        for name, ref in params.items():
+            sc = float(ref.grad.abs().max())
+            np.testing.assert_allclose(mine[name].grad.cpu().numpy(), ref.grad.cpu().numpy(), rtol=1e-3, atol=2e-4 * sc,
+                                       err_msg=name)
+    else:
+        # bf16 operands through three stacked convs and three batch-statistics normalisations over ~2 500 rows (whose
+        # backward subtracts means: cancellation).  Measured 7.4e-2 in the Frobenius norm for the input gradient, the
+        # same with torch's BatchNorm1d in place of the fused op (BEVFRONT_FUSED_BN_TRAIN=0): operand rounding, not the
+        # fusion.  The fp32 parametrisation above is the tight check of the arithmetic.
+        def close(a, b, what):
+            a, b = a.double().cpu().numpy(), b.double().cpu().numpy()
+            assert np.linalg.norm(a - b) <= 1.2e-1 * np.linalg.norm(b), (what, np.linalg.norm(a - b) / np.linalg.norm(b))
+            assert np.abs(a - b).max() <= 2.5e-1 * np.abs(b).max(), what
+
+        close(x.grad, xr.grad, "input gradient")
+        for name, ref in params.items():
+            close(mine[name].grad, ref.grad, name)
