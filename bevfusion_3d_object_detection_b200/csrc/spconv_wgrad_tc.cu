@@ -13,9 +13,9 @@
 //   Cin = 128          : M = one tap's two 64-channel slabs;
 // N = Cout, K = 16 rows per instruction.  A CTA owns 4 such "tap sets" (4 accumulators of Cout columns, at most 512 TMEM
 // columns) and a range of output rows; it streams the rows in chunks of R = 64 through a 2-3 stage ring:
-//   warps 0-3  producers: rulebook entries -> cp.async 16-byte gathers (zero-fill for missing pairs) straight into the
+//   warps 0-7  producers: rulebook entries -> cp.async 16-byte gathers (zero-fill for missing pairs) straight into the
 //              swizzled tiles, completion signalled on the stage's mbarrier (cp.async.mbarrier.arrive.noinc);
-//   warp 4     tcgen05.mma issuer (one elected lane), tcgen05.commit frees the stage;
+//   warp 8     tcgen05.mma issuer (one elected lane), tcgen05.commit frees the stage;
 //   warps 0-3  epilogue at the end: tcgen05.ld, fp32 atomics into d_W[Cout, kv, Cin] (several row ranges per tap group).
 // The fp32 FFMA kernel of spconv_bwd.cu stays as the fp32-parity path.
 #include <cuda.h>
@@ -27,7 +27,10 @@ namespace {
 
 constexpr int kR = 64;          // rows (K extent) of one chunk
 constexpr int kSets = 4;        // tap sets (accumulators) per CTA
-constexpr int kProd = 128;      // producer threads
+#ifndef BEVF_WG_PROD
+#define BEVF_WG_PROD 256
+#endif
+constexpr int kProd = BEVF_WG_PROD;   // producer threads (the first 128 also run the epilogue: one TMEM lane each)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(kProd + 32)
       if (++s == stages) { s = 0; ph ^= 1u; }
     }
     // ------------------------------------------ epilogue -------------------------------------------
+    if (warp < 4) {                            // warps 0-3 own the four TMEM lane quadrants
     mbar_wait(bar_done, 0u);
     tc_fence_after();
     const int m = warp * 32 + lane;                        // accumulator row (TMEM lane): (tap in set, ci) or ci
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(kProd + 32)
           }
         }
       }
+    }
     }
     tc_fence_before();
   } else {
