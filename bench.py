@@ -604,8 +604,9 @@ def run_frontend(args, rank, world, local_rank):
     # ---- training stage (configs[2]) inside the default line: one GPU's share, all-reduce active when N > 1 ----
     if args.config == "infer" and not args.no_train_stage:
         try:
-            stages["training"] = _train_measure(torch, dist, CONFIGS["train"], args.precision, dev, rank, world, steps=4,
-                                                warmup=2)["summary"]
+            torch.cuda.empty_cache()   # the eager training step allocates its temporaries: start from a clean cache
+            stages["training"] = _train_measure(torch, dist, CONFIGS["train"], args.precision, dev, rank, world, steps=6,
+                                                warmup=3)["summary"]
         except Exception as exc:
             print(f"[bench] training-stage timing unavailable: {exc}", file=sys.stderr)
 
