@@ -20,7 +20,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int N, bool TS, int NACC>
+template <int N, bool TS, int NACC, int AROT = 1>
 __global__ void __launch_bounds__(128) rate_kernel(long long *out, int reps) {
   __shared__ __align__(1024) uint8_t a_s[128 * 32];        // A: 128 rows x K = 16 bf16, 8 x 16 B core matrices
   __shared__ __align__(1024) uint8_t b_s[256 * 32];        // B: up to 256 rows x K = 16
@@ -52,9 +52,9 @@ __global__ void __launch_bounds__(128) rate_kernel(long long *out, int reps) {
       t0 = clock64();
       for (int r = 0; r < reps; ++r) {
         const uint32_t d = tmem + (uint32_t)((r % NACC) * N);
-        if (TS)
+        if (TS)   // AROT > 1: every MMA reads a different 8-column A slice (as the gather-GEMM does: one slice per tap and K step)
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                       ::"r"(d), "r"(a_t), "l"(bdesc), "r"(IDESC), "r"(1u) : "memory");
+                       ::"r"(d), "r"(a_t - (uint32_t)((r % AROT) * 8)), "l"(bdesc), "r"(IDESC), "r"(1u) : "memory");
         else
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(1u) : "memory");
@@ -74,17 +74,17 @@ __global__ void __launch_bounds__(128) rate_kernel(long long *out, int reps) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int N, bool TS, int NACC>
+template <int N, bool TS, int NACC, int AROT = 1>
 void run(const char *name, long long *d_out) {
   const int reps = 512;
   long long h[2];
   for (int it = 0; it < 2; ++it) {
-    rate_kernel<N, TS, NACC><<<148, 128>>>(d_out, reps);
+    rate_kernel<N, TS, NACC, AROT><<<148, 128>>>(d_out, reps);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s N=%d: %s\n", name, N, cudaGetErrorString(e)); return; }
   }
   cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("%s N=%3d accumulators=%d: issue %.1f clk/MMA, issue+drain %.1f clk/MMA (ideal math %d)\n", name, N, NACC,
+  printf("%s N=%3d accumulators=%d A slices=%d: issue %.1f clk/MMA, issue+drain %.1f clk/MMA (ideal math %d)\n", name, N, NACC, AROT,
          (double)h[0] / reps, (double)h[1] / reps, 128 * N / 256);
 }
 
@@ -96,5 +96,8 @@ int main() {
   run<16, false, 1>("SS", d_out); run<32, false, 1>("SS", d_out); run<64, false, 1>("SS", d_out);
   run<128, false, 1>("SS", d_out); run<256, false, 1>("SS", d_out);
   run<64, true, 2>("TS", d_out);  run<64, false, 2>("SS", d_out); run<128, true, 2>("TS", d_out);
+  // rotating A slices (16 distinct 8-column slices below column 480; accumulators stay below column 352)
+  run<16, true, 1, 16>("TS", d_out); run<32, true, 1, 16>("TS", d_out); run<64, true, 1, 16>("TS", d_out);
+  run<128, true, 1, 16>("TS", d_out); run<64, true, 2, 16>("TS", d_out);
   return 0;
 }
