@@ -527,8 +527,11 @@ def run_frontend(args, rank, world, local_rank):
     vox_bytes = 4 * c_pts * n_pts + m_vox * (4 * c_pts + 16 + 4)
     stages["voxelize_mean"] = dict(ms=ms_vox, bytes=vox_bytes, gbs=vox_bytes / ms_vox / 1e6,
                                    frac=vox_bytes / ms_vox / 1e6 / pk["hbm"], points=n_pts, voxels=m_vox,
-                                   timing="CUDA graph over %d distinct sweeps (sync-free C-ABI form), one frame per call"
-                                          % len(flat_pts))
+                                   timing="CUDA graph over %d distinct sweeps (sync-free C-ABI form), one frame per call; "
+                                          "the sweeps total %.0f MB, i.e. they stay L2-resident between replays (the op is bound "
+                                          "by L2 atomics / dependent latency, not by DRAM: profiles/README.md r2p; "
+                                          "scripts/vox_times.py times it over 128 MB of sweeps: same number)"
+                                          % (len(flat_pts), len(flat_pts) * flat_pts[0].numel() * 4 / 1e6))
 
     def f_pool(i):
         f = dev_b[i % ring]
