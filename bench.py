@@ -452,7 +452,7 @@ def run_frontend(args, rank, world, local_rank):
     def step_e2e(i):
         # host buffers in, host buffers out: H2D / compute / D2H on three streams, outputs multi-buffered
         f = pin_b[i % ring]
-        out_host["slot"] = pipe.submit(f["points"], f["depth"], f["ctx"], compact=args.compact_output)
+        out_host["slot"] = pipe.submit(f["points"], f["depth"], f["ctx"], output=args.output)
 
     def barrier():
         if world > 1:
@@ -489,11 +489,38 @@ def run_frontend(args, rank, world, local_rank):
     ms_e2e = timed(step_e2e, args.steps, args.warmup, fin=lambda: pipe.join())
     rep_e2e = [ms_e2e] + [timed(step_e2e, args.steps, 0, fin=lambda: pipe.join()) for _ in range(max(0, args.repeats - 1))]
     res_host = pipe.result(out_host["slot"])
-    lid_h, cam_h = res_host[0], res_host[1]
+    rows_mode = args.output == "rows"
+    if rows_mode:   # --output rows: the headline e2e itself uses the lossless rows form
+        d2h_rows = int(res_host.nbytes())
+        lid_h, cam_h = res_host.dense()
+    else:
+        lid_h, cam_h = res_host[0], res_host[1]
+    # the same pipeline with the LOSSLESS "rows" output (active rows + coordinates instead of the dense maps; the pack
+    # kernels store straight into the pinned host buffers): reported beside the headline e2e, which keeps the dense maps
+    e2e_rows = None
+    try:
+        def step_rows(i):
+            f = pin_b[i % ring]
+            out_host["rows_slot"] = pipe.submit(f["points"], f["depth"], f["ctx"], output="rows")
+
+        ms_rows = timed(step_rows, args.steps, args.warmup, fin=lambda: pipe.join())
+        rr = pipe.result(out_host["rows_slot"])
+        lid_r, cam_r = rr.dense()
+        f_last = pin_b[(args.warmup + args.steps - 1) % ring]
+        lid_d, cam_d = pipe.result(pipe.submit(f_last["points"], f_last["depth"], f_last["ctx"]))   # dense maps of the same frame
+        e2e_rows = dict(value=world * B * args.steps / (ms_rows / 1e3), unit="frames/s", ms_per_step=ms_rows / args.steps,
+                        d2h_bytes_per_step=int(rr.nbytes()), h2d_bytes_per_step=None,
+                        lossless=bool(torch.equal(lid_r, lid_d) and torch.equal(cam_r, cam_d)),
+                        output="fp32 active rows + coordinates (LiDAR map), fp32 columns of the reached cells (camera map); "
+                               "dense maps rebuilt on the host bit for bit (`lossless`)")
+    except Exception as exc:   # never let the extra block take the headline line down
+        print(f"[bench] rows-output timing unavailable: {exc}", file=sys.stderr)
     assert bool(torch.isfinite(lid_h.float()).all()) and float(cam_h.float().abs().sum()) > 0.0
     h2d = sum(int(v.numel() * v.element_size()) for v in pin_b[0]["points"]) + \
         int(pin_b[0]["depth"].numel() * 4 + pin_b[0]["ctx"].numel() * 4)
-    d2h = int(sum(t.numel() * t.element_size() for t in res_host))
+    if e2e_rows is not None:
+        e2e_rows["h2d_bytes_per_step"] = h2d
+    d2h = d2h_rows if rows_mode else int(sum(t.numel() * t.element_size() for t in res_host))
     # raw host-link ceiling for exactly these bytes, all ranks copying at once (what bounds e2e at N = 8)
     barrier()
     link_gbs, link_ms = hostlink_gbs(torch, dev, h2d, d2h)
@@ -667,12 +694,15 @@ def run_frontend(args, rank, world, local_rank):
                             l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (ring, ring * B * frame_bytes / 1e6),
                             parallelism="frame-parallel, no data-path collective"),
                 e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=ms_e2e / args.steps, output=("compact" if args.compact_output else "fp32 dense BEV maps"),
+                         ms_per_step=ms_e2e / args.steps, output={"dense": "fp32 dense BEV maps", "bf16": "compact (bf16 dense maps, lossy)",
+                                 "rows": "lossless fp32 rows: active LiDAR rows + coordinates, camera columns of the "
+                                         "reached cells"}[args.output],
                          median_value=world * B * args.steps / (med_e2e / 1e3),
                          hostlink=dict(gbs_all_ranks=link_total, gbs_this_rank=link_gbs, ms_per_step_copies_only=link_ms,
                                        ceiling_frames_per_s=world * B * 1e3 / link_ms,
                                        note="raw pinned H2D+D2H of exactly these bytes on two streams, all ranks at "
                                             "once: the host-link ceiling of e2e")),
+                e2e_rows=e2e_rows,
                 repeats=dict(n=len(rep_ms), value_median=world * B * args.steps / (med / 1e3),
                              value_min=world * B * args.steps / (max(rep_ms) / 1e3),
                              value_max=world * B * args.steps / (min(rep_ms) / 1e3)),
@@ -1050,11 +1080,16 @@ def main():
     ap.add_argument("--no-train-stage", action="store_true", help="skip stages.training of the default line")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of K steps each (median reported beside the first)")
     ap.add_argument("--compact-output", action="store_true",
-                    help="e2e: copy the BEV maps to the host as bf16 instead of fp32 (opt-in; halves the D2H bytes)")
+                    help="e2e: copy the BEV maps to the host as bf16 instead of fp32 (opt-in, lossy; = --output bf16)")
+    ap.add_argument("--output", default=None, choices=["dense", "rows", "bf16"],
+                    help="form in which e2e returns the BEV maps to the host: dense fp32 maps (default, the reference's "
+                         "tensors), lossless rows (active rows + coordinates, 2.4x fewer bytes), or bf16 dense maps")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight per GPU: plans of the host pipeline")
     ap.add_argument("--inflight-device", type=int, default=2,
                     help="batches in flight for the device-resident measurement (<= --inflight; measured best at 2)")
     args = ap.parse_args()
+    if args.output is None:
+        args.output = "bf16" if args.compact_output else "dense"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

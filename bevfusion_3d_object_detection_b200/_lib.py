@@ -19,7 +19,7 @@ def _declare(lib):
     c_int, c_void_p, c_size_t = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
     lib.bevf_last_error.restype = ctypes.c_char_p
     for name in ("bevf_hard_voxelize_workspace_bytes", "bevf_dynamic_scatter_workspace_bytes",
-                 "bevf_bev_pool_workspace_bytes", "bevf_spconv_index_bytes"):
+                 "bevf_bev_pool_workspace_bytes", "bevf_spconv_index_bytes", "bevf_pack_sparse_rows_bytes"):
         if hasattr(lib, name):
             getattr(lib, name).restype = c_size_t
     lib.bevf_spconv_index_error_flag.restype = c_void_p

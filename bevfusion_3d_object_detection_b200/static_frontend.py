@@ -323,6 +323,8 @@ class StaticFrontEnd:
         c_last = self.ops[-1]["conv"].out_channels
         check(L.bevf_sparse_to_dense(ptr(cur["f32"]), ptr(last.indices), last.cap, ptr(last.n_dev), c_last, self.batch,
                                      last.shape_c, ptr(self.lidar_bev), 1, st))
+        # the same information as active rows (HostPipeline's lossless "rows" output reads these)
+        self.last_rows, self.last_level = cur["f32"], last
         # 6. camera branch (already in flight on its own stream when overlapping)
         if self.overlap:
             main.wait_event(cam_done)

@@ -412,6 +412,26 @@ int bevf_bn_train_backward(const float *x, const float *dy, const float *y, cons
                            const float *save_invstd, int n, int c, int relu, double *sums_ws, float *dx, void *dx_bf16,
                            float *d_residual, float *dgamma, float *dbeta, void *stream);
 
+/*
+ * Lossless "occupied rows" form of the two BEV maps (extension; the reference keeps its maps on the device for the fuser,
+ * bevfusion.py:300-330 -- this is for a caller that wants them on the host).  `dst` may be device memory or PINNED HOST
+ * memory (device-visible at its own address under unified addressing): the kernels then store straight over the host
+ * link and only the occupied rows travel.
+ *   bevf_pack_sparse_rows: the active rows of a sparse tensor (BEVFusionSparseEncoder's last level before dense(),
+ *     projects/BEVFusion/bevfusion/sparse_encoder.py:147-151):
+ *       dst = int32 header {n, c, cap, 0} | int32 indices [cap, 4] | fp32 rows [cap, c]     (the first n rows are written)
+ *     n is read on the device (min(*n_dev, cap)); c % 4 == 0; bevf_pack_sparse_rows_bytes(cap, c) = bytes of dst.
+ *   bevf_pack_cells: columns of a dense [B, nz*C, nx, ny] map at the given cells (cell = (b*nz + z)*nx*ny + x*ny + y, e.g.
+ *     the `interval_cell` table of bev_pool: the camera map is zero everywhere else): dst[ch, i] = value of channel ch at
+ *     cells[i]; pitch (floats, multiple of 4, >= n_cells rounded up to 4) between channels.
+ * max_blocks > 0 caps the grid (the CTAs are 64 threads so that they fit next to other resident kernels).
+ */
+size_t bevf_pack_sparse_rows_bytes(int cap, int c);
+int bevf_pack_sparse_rows(const float *feats, const int *indices, int cap, const int *n_dev, int c, void *dst,
+                          size_t dst_bytes, int max_blocks, void *stream);
+int bevf_pack_cells(const float *dense, const int *cells, int n_cells, int c, int nz, int plane, float *dst, int pitch,
+                    int max_blocks, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,38 @@ def test_empty_and_tiny_frames():
             assert float(gl.abs().max()) == 0.0
         else:
             assert float(gl.abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("batch,mode", [(1, "rows"), (2, "rows"), (1, "rows_zero_copy")])
+def test_host_pipeline_rows_output_is_lossless(batch, mode):
+    """HostPipeline's "rows" output (active rows + coordinates written into pinned host buffers by the pack kernels)
+    rebuilds, on the host, the dense fp32 maps of the default output bit for bit; frame after frame on every slot."""
+    torch.manual_seed(2)
+    model = frontend.BEVFrontEnd(precision="bf16").cuda().eval()
+    rig = {k: torch.from_numpy(v).cuda() for k, v in synthetic.camera_rig(6, (256, 704), batch).items()}
+    tables = model.set_calibration(rig)
+    frames = []
+    for i in range(4):
+        pts = [torch.from_numpy(synthetic.lidar_sweeps(n_sweeps=[2, 5, 1, 3][i], seed=60 + 7 * i + k)).pin_memory()
+               for k in range(batch)]
+        depth, ctx = synthetic.camera_features(6, 118, 80, (32, 88), batch=batch, seed=60 + i)
+        frames.append((pts, torch.from_numpy(depth).pin_memory(), torch.from_numpy(ctx).pin_memory()))
+    pipe = frontend.HostPipeline(model, tables, "cuda", depth=2, batch=batch, max_points=200000,
+                                 example=([p.cuda() for p in frames[1][0]], frames[1][1].cuda(), frames[1][2].cuda()))
+    dense = []
+    for pts, depth, ctx in frames:
+        lid, cam = pipe.result(pipe.submit(pts, depth, ctx))
+        dense.append((lid.clone(), cam.clone()))
+    slots = [pipe.submit(pts, depth, ctx, output=mode) for pts, depth, ctx in frames[:2]]   # two frames in flight
+    got = [pipe.result(s).dense() for s in slots]
+    for pts, depth, ctx in frames[2:]:
+        got.append(pipe.result(pipe.submit(pts, depth, ctx, output=mode)).dense())
+    for (wl, wc), (gl, gc) in zip(dense, got):
+        assert torch.equal(gl, wl) and torch.equal(gc, wc)
+    r = pipe.result(pipe.submit(*frames[0], output=mode))
+    idx, rows = r.lidar()
+    assert idx.shape[0] == rows.shape[0] > 0 and rows.shape[1] == 128 and int(idx[:, 0].max()) == batch - 1
+    assert r.nbytes() < 0.6 * (dense[0][0].numel() + dense[0][1].numel()) * 4
+    # mixing output forms on one pipeline keeps working
+    lid, cam = pipe.result(pipe.submit(*frames[3]))
+    assert torch.equal(lid, dense[3][0]) and torch.equal(cam, dense[3][1])
