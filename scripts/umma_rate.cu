@@ -20,14 +20,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int N, bool TS, int NACC, int AROT = 1>
+template <int N, bool TS, int NACC, int AROT = 1, int BSBO = 0>
 __global__ void __launch_bounds__(128) rate_kernel(long long *out, int reps) {
   __shared__ __align__(1024) uint8_t a_s[128 * 32];        // A: 128 rows x K = 16 bf16, 8 x 16 B core matrices
-  __shared__ __align__(1024) uint8_t b_s[256 * 32];        // B: up to 256 rows x K = 16
+  __shared__ __align__(1024) uint8_t b_s[32 * 1024];       // B: up to 256 rows x K = 16 (or the gather-GEMM's weight-tile layout, BSBO > 0)
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
   for (int i = threadIdx.x; i < 128 * 32 / 4; i += 128) reinterpret_cast<uint32_t *>(a_s)[i] = 0;
-  for (int i = threadIdx.x; i < 256 * 32 / 4; i += 128) reinterpret_cast<uint32_t *>(b_s)[i] = 0;
+  for (int i = threadIdx.x; i < 32 * 1024 / 4; i += 128) reinterpret_cast<uint32_t *>(b_s)[i] = 0;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(128) rate_kernel(long long *out, int reps) {
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   if (warp == 0) {
     const uint64_t adesc = make_desc(smem_u32(a_s), 2048u, 128u);
-    const uint64_t bdesc = make_desc(smem_u32(b_s), (uint32_t)(N / 8) * 128u, 128u);
+    // BSBO == 0: the 8-row groups of B are contiguous (SBO = 128 B) and the second K chunk follows them (LBO = N/8 * 128 B);
+    // BSBO > 0: the gather-GEMM's weight tile [N/8][Cin/8][8 x 16 B]: K chunks adjacent (LBO = 128 B), row groups BSBO bytes apart
+    const uint64_t bdesc = BSBO ? make_desc(smem_u32(b_s), 128u, (uint32_t)BSBO) : make_desc(smem_u32(b_s), (uint32_t)(N / 8) * 128u, 128u);
     const uint32_t a_t = tmem + 480u;     // 8 columns of A behind the accumulators (NACC * N <= 480)
     long long t0 = 0, t1 = 0, t2 = 0;
     if (elect_one()) {
@@ -74,17 +76,17 @@ __global__ void __launch_bounds__(128) rate_kernel(long long *out, int reps) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int N, bool TS, int NACC, int AROT = 1>
+template <int N, bool TS, int NACC, int AROT = 1, int BSBO = 0>
 void run(const char *name, long long *d_out) {
   const int reps = 512;
   long long h[2];
   for (int it = 0; it < 2; ++it) {
-    rate_kernel<N, TS, NACC, AROT><<<148, 128>>>(d_out, reps);
+    rate_kernel<N, TS, NACC, AROT, BSBO><<<148, 128>>>(d_out, reps);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s N=%d: %s\n", name, N, cudaGetErrorString(e)); return; }
   }
   cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("%s N=%3d accumulators=%d A slices=%d: issue %.1f clk/MMA, issue+drain %.1f clk/MMA (ideal math %d)\n", name, N, NACC, AROT,
+  printf("%s N=%3d accumulators=%d A slices=%d B row-group stride=%d: issue %.1f clk/MMA, issue+drain %.1f clk/MMA (ideal math %d)\n", name, N, NACC, AROT, BSBO ? BSBO : 128,
          (double)h[0] / reps, (double)h[1] / reps, 128 * N / 256);
 }
 
@@ -99,5 +101,8 @@ int main() {
   // rotating A slices (16 distinct 8-column slices below column 480; accumulators stay below column 352)
   run<16, true, 1, 16>("TS", d_out); run<32, true, 1, 16>("TS", d_out); run<64, true, 1, 16>("TS", d_out);
   run<128, true, 1, 16>("TS", d_out); run<64, true, 2, 16>("TS", d_out);
+  // the gather-GEMM's weight-tile layout: row groups Cin/8 * 128 bytes apart (Cin = 32 / 64 / 128)
+  run<32, true, 1, 16, 512>("TS", d_out); run<64, true, 1, 16, 1024>("TS", d_out); run<128, true, 1, 16, 2048>("TS", d_out);
+  run<64, true, 1, 16, 512>("TS", d_out); run<128, true, 1, 16, 1024>("TS", d_out);
   return 0;
 }
