@@ -383,6 +383,10 @@ int bevf_spconv_tc_supported(int cin, int cout);
  * the register-gather kernel (mma.sync fragments loaded straight from L2, spconv_rg.cu): same products, fp32 sums in a
  * different order.  variant < 0 only queries.  Returns the previous setting; process-wide (also env BEVFRONT_TC_TS). */
 int bevf_spconv_tc_variant(int variant);
+/* Persistent CTAs per tensor-core gather-GEMM launch: 0 (default) = one per SM; a smaller number leaves SMs to the launches
+ * of another stream (two frames in flight on half the SMs each).  Returns the previous value; a negative argument only
+ * queries.  Process-wide; read at launch (i.e. at graph capture). */
+int bevf_spconv_tc_max_ctas(int max_ctas);
 int bevf_spconv_cast_bf16(const float *src, void *dst_bf16, int n, int cin, int cin_pad, const int *n_dev,
                           void *stream);
 int bevf_spconv_pack_weight_bf16(const float *weight_okc, void *weight_packed, int kv, int cin, int cout,
