@@ -203,3 +203,44 @@ def test_encoder_layout_and_state_dict_keys():
     assert tuple(by_name["encoder_layers.encoder_layer4.0.conv1"].weight.shape) == (128, 3, 3, 3, 128)
     n_params = sum(p.numel() for p in enc.parameters())
     assert 2.5e6 < n_params < 3.0e6   # ~2.7 M parameters
+
+
+def test_rows_result_rebuilds_dense_maps_on_the_host():
+    """frontend.RowsResult (host side of HostPipeline's lossless "rows" output): header | indices | rows buffer layout of
+    bevf_pack_sparse_rows and the channel-major camera columns of bevf_pack_cells scatter back into
+    [B, C*Z, X, Y] / [B, nz*C, nx, ny] exactly as SparseConvTensor.dense() + permute + view (sparse_encoder.py:147-151) and
+    bev_pool's output layout (depth_lss.py:199-204) define them."""
+    import torch
+
+    from bevfusion_3d_object_detection_b200.frontend import RowsResult
+
+    rng = np.random.default_rng(0)
+    B, C, Z, X, Y, cap, n = 2, 8, 2, 5, 6, 40, 23
+    lin = rng.choice(B * X * Y * Z, size=n, replace=False)
+    idx = np.stack([lin // (X * Y * Z), (lin // (Y * Z)) % X, (lin // Z) % Y, lin % Z], 1).astype(np.int32)
+    rows = rng.standard_normal((n, C)).astype(np.float32)
+    raw = torch.zeros(16 + cap * 16 + cap * C * 4, dtype=torch.uint8)
+    raw[:16].view(torch.int32)[:] = torch.tensor([n, C, cap, 0], dtype=torch.int32)
+    raw[16:16 + cap * 16].view(torch.int32).view(cap, 4)[:n] = torch.from_numpy(idx)
+    raw[16 + cap * 16:].view(torch.float32).view(cap, C)[:n] = torch.from_numpy(rows)
+    nz, Cc, nx, ny = 2, 3, 4, 7
+    cells_all = B * nz * nx * ny
+    cells = np.sort(rng.choice(cells_all, size=17, replace=False)).astype(np.int32)
+    pitch = (len(cells) + 3) // 4 * 4
+    cols = torch.zeros((Cc, pitch), dtype=torch.float32)
+    cols[:, :len(cells)] = torch.from_numpy(rng.standard_normal((Cc, len(cells))).astype(np.float32))
+    r = RowsResult(raw, cols, cap, C, torch.from_numpy(cells), len(cells), (B, C * Z, X, Y), (B, nz * Cc, nx, ny), nz)
+    gi, gr = r.lidar()
+    assert gi.shape == (n, 4) and torch.equal(gr, torch.from_numpy(rows))
+    lidar, cam = r.dense()
+    want_l = np.zeros((B, C, Z, X, Y), np.float32)
+    for (b, x, y, z), row in zip(idx, rows):
+        want_l[b, :, z, x, y] = row                      # dense() [N, C, X, Y, Z] -> permute(0, 1, 4, 2, 3)
+    np.testing.assert_array_equal(lidar.numpy(), want_l.reshape(B, C * Z, X, Y))
+    want_c = np.zeros((B, nz * Cc, nx, ny), np.float32)
+    for i, cell in enumerate(cells):
+        bz, xy = divmod(int(cell), nx * ny)
+        b, z = divmod(bz, nz)
+        want_c[b, z * Cc:(z + 1) * Cc, xy // ny, xy % ny] = cols[:, i].numpy()
+    np.testing.assert_array_equal(cam.numpy(), want_c)
+    assert r.nbytes() == 16 + n * 16 + n * C * 4 + Cc * pitch * 4
