@@ -621,7 +621,12 @@ def run_frontend(args, rank, world, local_rank):
     tr, tr_name = latest_traffic()
     if args.precision == "bf16" and args.config == "infer" and tr is not None:
         roof["traffic"] = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / n_gemm
-        roof["traffic_note"] = "DRAM bytes per launch, mean over the frame's launches (profiles/%s)" % tr_name
+        roof["traffic_note"] = ("DRAM bytes per launch, mean over the frame's launches (profiles/%s; ncu flushes the caches "
+                                "before every kernel: cold-cache figure)" % tr_name)
+        warm = os.path.join(ROOT, "profiles", "r2z_gemm_warm_dram.json")
+        if os.path.exists(warm):   # same capture with --cache-control none: the launches back to back, as in the frame
+            tw = json.load(open(warm))
+            roof["traffic_no_flush"] = (tw["dram_read_bytes"] + tw["dram_write_bytes"]) / n_gemm
 
     # ---- fp32 parity mode (reference precision, bevfusion.py:177,201 runs the encoder with autocast off) -------
     fp32_block = None
