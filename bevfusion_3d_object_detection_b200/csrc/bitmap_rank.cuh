@@ -151,9 +151,9 @@ int rank_build(const unsigned *bitmap, long long nwords, int *word_prefix, int *
 constexpr int kRankMaxChunks = 592;
 
 template <typename Emit>
-__global__ void __launch_bounds__(kRankThreads)
-    rank_chunk_scan_kernel(const unsigned *__restrict__ bitmap, long long nwords, long long chunk_words, int nchunks,
-                           int *__restrict__ sync, int *__restrict__ word_prefix, int *__restrict__ total, Emit emit) {
+__device__ __forceinline__ void rank_chunk_scan_body(const unsigned *__restrict__ bitmap, long long nwords,
+                                                     long long chunk_words, int nchunks, int *__restrict__ sync,
+                                                     int *__restrict__ word_prefix, int *__restrict__ total, Emit emit) {
   __shared__ int ws[kRankThreads / 32];
   __shared__ int s_tile, s_val;
   int *counter = sync, *status = sync + 1;
@@ -231,6 +231,43 @@ __global__ void __launch_bounds__(kRankThreads)
     }
     run_base += ttot;
   }
+}
+
+template <typename Emit>
+__global__ void __launch_bounds__(kRankThreads)
+    rank_chunk_scan_kernel(const unsigned *__restrict__ bitmap, long long nwords, long long chunk_words, int nchunks,
+                           int *__restrict__ sync, int *__restrict__ word_prefix, int *__restrict__ total, Emit emit) {
+  rank_chunk_scan_body(bitmap, nwords, chunk_words, nchunks, sync, word_prefix, total, emit);
+}
+
+// several independent bitmaps in ONE launch: blockIdx.y selects the segment (each with its own ticket / status words)
+constexpr int kRankMaxSegments = 6;
+struct RankSegment {
+  const unsigned *bitmap;
+  long long nwords, chunk_words;
+  int nchunks;
+  int *sync, *word_prefix, *total;
+};
+struct RankSegments {
+  int n;
+  RankSegment seg[kRankMaxSegments];
+};
+inline void rank_plan_chunks(long long nwords, long long &chunk_words, int &nchunks) {
+  long long nc = (nwords + kRankTile - 1) / kRankTile;
+  if (nc > kRankMaxChunks) nc = kRankMaxChunks;
+  if (nc < 1) nc = 1;
+  chunk_words = (nwords + nc - 1) / nc;
+  chunk_words = (chunk_words + kRankTile - 1) / kRankTile * kRankTile;
+  nc = (nwords + chunk_words - 1) / chunk_words;
+  nchunks = nc < 1 ? 1 : (int)nc;
+}
+struct RankEmitNothing {
+  __device__ void operator()(int, unsigned long long) const {}
+};
+static __global__ void __launch_bounds__(kRankThreads) rank_chunk_scan_multi_kernel(const __grid_constant__ RankSegments S) {
+  const RankSegment &g = S.seg[blockIdx.y];
+  if ((int)blockIdx.x >= g.nchunks) return;      // whole CTA (tickets are taken by the first nchunks CTAs of the segment only)
+  rank_chunk_scan_body(g.bitmap, g.nwords, g.chunk_words, g.nchunks, g.sync, g.word_prefix, g.total, RankEmitNothing{});
 }
 
 // `sync` must hold 1 + kRankMaxChunks zeroed ints

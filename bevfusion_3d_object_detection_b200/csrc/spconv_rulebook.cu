@@ -297,6 +297,110 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- all strided levels of a chain from the level-0 coordinates ---------------------------------------------------------
+// The sites of a strided level are the cells some site of the level below reaches; for ONE site the reachable outputs are,
+// per axis, the interval ceil((c + p - (k-1)) / s) .. floor((c + p) / s) clipped to the grid, for a full interval of
+// inputs [i0, i1] the interval ceil((i0 + p - (k-1)) / s) .. floor((i1 + p) / s) -- so the box a level-0 site reaches on
+// level l follows from its box on level l-1 (every cell of which is active, being reached by that very site), and level l's
+// site set is the union of the boxes of all level-0 sites.  One pass over the level-0 coordinates therefore fills the
+// bitmaps of ALL levels; their rank scans and site lists are then independent and go out as one multi-segment launch each
+// (per level before: mark + scan + emit + three memory operations, each waiting for the level below).  Dilation 1.
+constexpr int kMaxChain = bevf::kRankMaxSegments;
+struct ChainLevel {
+  int k[3], s[3], p[3];
+  Grid og;
+  unsigned *bitmap;
+  const int *word_prefix;
+  const int *total;
+  long long nwords;
+  int *out_indices;
+  int cap;
+  int *n_out_dev;
+};
+struct ChainArgs {
+  int nlev;
+  Grid g0;
+  ChainLevel lv[kMaxChain];
+};
+
+__device__ __forceinline__ int ceil_div_i(int a, int s) { return a >= 0 ? (a + s - 1) / s : -((-a) / s); }
+__device__ __forceinline__ int floor_div_i(int a, int s) { return a >= 0 ? a / s : -((-a + s - 1) / s); }
+
+__global__ void __launch_bounds__(256)
+    mark_levels_kernel(const int *__restrict__ coords0, int n, const int *__restrict__ n_dev, const __grid_constant__ ChainArgs A) {
+  if (n_dev) n = min(n, *n_dev);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(coords0) + i);   // (b, x, y, z)
+    if ((unsigned)c.x >= (unsigned)A.g0.b || (unsigned)c.y >= (unsigned)A.g0.x || (unsigned)c.z >= (unsigned)A.g0.y ||
+        (unsigned)c.w >= (unsigned)A.g0.z)
+      continue;                                                          // reported by the level-0 index build
+    int lo[3] = {c.y, c.z, c.w}, hi[3] = {c.y, c.z, c.w};
+    for (int l = 0; l < A.nlev; ++l) {
+      const ChainLevel &L = A.lv[l];
+      const int lim[3] = {L.og.x, L.og.y, L.og.z};
+      bool empty = false;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int nlo = max(ceil_div_i(lo[a] + L.p[a] - (L.k[a] - 1), L.s[a]), 0);
+        const int nhi = min(floor_div_i(hi[a] + L.p[a], L.s[a]), lim[a] - 1);
+        lo[a] = nlo; hi[a] = nhi;
+        empty |= nlo > nhi;
+      }
+      if (empty) break;
+      for (int x = lo[0]; x <= hi[0]; ++x) {
+        for (int y = lo[1]; y <= hi[1]; ++y) {
+          const unsigned long long base = (((unsigned long long)c.x * L.og.x + x) * L.og.y + y) * L.og.z;
+          unsigned long long cur_w = ~0ull;
+          unsigned mask = 0u;
+          for (int z = lo[2]; z <= hi[2]; ++z) {                         // the z run of one (x, y): one or two bitmap words
+            const unsigned long long cell = base + (unsigned)z, w = cell >> 5;
+            if (w != cur_w) {
+              if (mask && (L.bitmap[cur_w] & mask) != mask) atomicOr(L.bitmap + cur_w, mask);
+              cur_w = w;
+              mask = 0u;
+            }
+            mask |= 1u << (unsigned)(cell & 31);
+          }
+          if (mask && (L.bitmap[cur_w] & mask) != mask) atomicOr(L.bitmap + cur_w, mask);
+        }
+      }
+    }
+  }
+}
+
+// site lists of all levels of a chain: blockIdx.y = level (same per-word walk as emit_sites_kernel)
+__global__ void __launch_bounds__(256) emit_sites_multi_kernel(const __grid_constant__ ChainArgs A) {
+  const ChainLevel &L = A.lv[blockIdx.y];
+  const Grid og = L.og;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && L.n_out_dev) *L.n_out_dev = *L.total;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < L.nwords; w += (long long)gridDim.x * blockDim.x) {
+    unsigned bits = __ldg(L.bitmap + w);
+    if (!bits) continue;
+    int rank = __ldg(L.word_prefix + w);
+    unsigned long long key = (unsigned long long)w << 5;
+    int z0 = (int)(key % (unsigned long long)og.z); key /= (unsigned long long)og.z;
+    int y0 = (int)(key % (unsigned long long)og.y); key /= (unsigned long long)og.y;
+    int x0 = (int)(key % (unsigned long long)og.x); key /= (unsigned long long)og.x;
+    int b0 = (int)key;
+    int last = 0;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      z0 += b - last;
+      last = b;
+      while (z0 >= og.z) {
+        z0 -= og.z;
+        if (++y0 >= og.y) {
+          y0 = 0;
+          if (++x0 >= og.x) { x0 = 0; ++b0; }
+        }
+      }
+      if (rank < L.cap) reinterpret_cast<int4 *>(L.out_indices)[rank] = make_int4(b0, x0, y0, z0);
+      rank += 1;
+    }
+  }
+}
+
 // strided conv, pass 2: for every output site and tap, look the input up
 template <typename IT>
 __global__ void __launch_bounds__(256)
@@ -583,6 +687,77 @@ BEVF_API int bevf_spconv_strided_sites(const int *in_indices, int n_in, const in
   }
   if (n_out_dev)
     BEVF_CHECK_CUDA(cudaMemcpyAsync(n_out_dev, m.scalars, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return BEVF_OK;
+}
+
+BEVF_API int bevf_spconv_strided_sites_chain(const int *coords0, int n0, const int *n0_dev, int batch, const int *shape0,
+                                             int nlev, const int *ksizes, const int *strides, const int *paddings,
+                                             void *const *index_mems, const size_t *index_bytes, int *const *out_indices,
+                                             const int *caps, int *const *n_out_devs, void *stream) {
+  BEVF_CHECK_ARG(nlev >= 1 && nlev <= kMaxChain, "a chain has 1..%d strided levels (got %d)", kMaxChain, nlev);
+  BEVF_CHECK_ARG(n0 >= 0 && (n0 == 0 || coords0) && ksizes && strides && paddings && index_mems && index_bytes &&
+                     out_indices && caps && n_out_devs, "NULL argument");
+  BEVF_CHECK_ARG((reinterpret_cast<uintptr_t>(coords0) & 15u) == 0, "coordinates must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  ChainArgs A;
+  bevf::RankSegments S;
+  A.nlev = S.n = nlev;
+  A.g0 = Grid{batch, shape0[0], shape0[1], shape0[2]};
+  int shape[3] = {shape0[0], shape0[1], shape0[2]};
+  const int ones[3] = {1, 1, 1};
+  int max_chunks = 1;
+  long long max_words = 1;
+  for (int l = 0; l < nlev; ++l) {
+    const int *k = ksizes + 3 * l, *sd = strides + 3 * l, *pd = paddings + 3 * l;
+    int rc = check_geom(k, sd, pd, ones);
+    if (rc) return rc;
+    int os[3];
+    bevf_spconv_out_shape(shape, k, sd, pd, ones, os);
+    long long nwords;
+    rc = grid_words(batch, os, nwords);
+    if (rc) return rc;
+    IndexMem m;
+    const size_t need = carve_index(m, index_mems[l], index_bytes[l], nwords);
+    if (!index_mems[l] || need > index_bytes[l]) {
+      bevf::set_error("spconv index memory of chain level %d too small: need %zu bytes, got %zu", l + 1, need, index_bytes[l]);
+      return BEVF_ERR_WORKSPACE;
+    }
+    BEVF_CHECK_ARG(out_indices[l] && (reinterpret_cast<uintptr_t>(out_indices[l]) & 15u) == 0, "bad out_indices of level %d", l + 1);
+    // scalars (total, error flag, scan ticket + flags) and the bitmap are adjacent: one clear
+    const size_t clear = (size_t)(reinterpret_cast<char *>(m.bitmap + nwords) - reinterpret_cast<char *>(m.scalars));
+    BEVF_CHECK_CUDA(cudaMemsetAsync(m.scalars, 0, clear, st));
+    ChainLevel &L = A.lv[l];
+    for (int j = 0; j < 3; ++j) { L.k[j] = k[j]; L.s[j] = sd[j]; L.p[j] = pd[j]; shape[j] = os[j]; }
+    L.og = Grid{batch, os[0], os[1], os[2]};
+    L.bitmap = m.bitmap;
+    L.word_prefix = m.word_prefix;
+    L.total = m.scalars;
+    L.nwords = nwords;
+    L.out_indices = out_indices[l];
+    L.cap = caps[l];
+    L.n_out_dev = n_out_devs[l];
+    bevf::RankSegment &R = S.seg[l];
+    R.bitmap = m.bitmap;
+    R.nwords = nwords;
+    bevf::rank_plan_chunks(nwords, R.chunk_words, R.nchunks);
+    R.sync = m.scalars + 64;
+    R.word_prefix = m.word_prefix;
+    R.total = m.scalars;
+    if (R.nchunks > max_chunks) max_chunks = R.nchunks;
+    if (nwords > max_words) max_words = nwords;
+  }
+  if (n0 > 0) {
+    const int blocks = bevf::ceil_div(n0, 256) < kRbBlocks ? bevf::ceil_div(n0, 256) : kRbBlocks;
+    mark_levels_kernel<<<blocks, 256, 0, st>>>(coords0, n0, n0_dev, A);
+    BEVF_CHECK_LAUNCH();
+  }
+  bevf::rank_chunk_scan_multi_kernel<<<dim3(max_chunks, nlev), bevf::kRankThreads, 0, st>>>(S);
+  BEVF_CHECK_LAUNCH();
+  {
+    const int blocks = (int)(bevf::ceil_div(max_words, 256) < kRbBlocks ? bevf::ceil_div(max_words, 256) : kRbBlocks);
+    emit_sites_multi_kernel<<<dim3(blocks, nlev), 256, 0, st>>>(A);
+    BEVF_CHECK_LAUNCH();
+  }
   return BEVF_OK;
 }
 

@@ -81,6 +81,7 @@ class StaticFrontEnd:
         self.levels = [_Level(cap0, enc.sparse_shape, self.batch, dev)]
         self.perm0 = torch.empty(cap0, dtype=torch.int32, device=dev)
         self._plan_levels()
+        self._plan_chain()
         self._alloc_features()
         # ---- camera branch ------------------------------------------------------------------------------------
         self.depth = None
@@ -148,6 +149,30 @@ class StaticFrontEnd:
                 op["pair"] = level.subm_pairs[key]
                 op["subm_key"] = key
             op["level_out"] = lvl
+
+    def _plan_chain(self):
+        """Arguments of bevf_spconv_strided_sites_chain: the output sites of ALL strided levels in three launches from the
+        level-0 coordinates (instead of mark + scan + emit per level, each waiting for the level below).  Used when every
+        strided conv has dilation 1 (the encoder's do); BEVFRONT_SITES_CHAIN=0 keeps the level-by-level calls."""
+        import os
+
+        strided = [op for op in self.ops if not op["conv"].subm]
+        ok = (os.environ.get("BEVFRONT_SITES_CHAIN", "1") == "1" and 1 <= len(strided) <= 6
+              and all(tuple(op["conv"].dilation) == (1, 1, 1) for op in strided)
+              and [op["level_out"] for op in strided] == list(range(1, len(strided) + 1)))
+        self.chain = None
+        if not ok:
+            return
+        n = len(strided)
+        flat = lambda key: (ctypes.c_int * (3 * n))(*[int(v) for op in strided for v in getattr(op["conv"], key)])
+        lv = [self.levels[op["level_out"]] for op in strided]
+        self.chain = dict(
+            n=n, ks=flat("kernel_size"), st=flat("stride"), pd=flat("padding"),
+            mems=(ctypes.c_void_p * n)(*[l.index_mem.data_ptr() for l in lv]),
+            bytes=(ctypes.c_size_t * n)(*[l.index_bytes for l in lv]),
+            outs=(ctypes.c_void_p * n)(*[l.indices.data_ptr() for l in lv]),
+            caps=(ctypes.c_int * n)(*[l.cap for l in lv]),
+            ndevs=(ctypes.c_void_p * n)(*[l.n_dev.data_ptr() for l in lv]))
 
     def _alloc_features(self):
         """Three rotating feature slots per level (block input / hidden / output), fp32 and (bf16 path) bf16."""
@@ -241,6 +266,15 @@ class StaticFrontEnd:
         rule_stream = self.s_rule if self.overlap else main
         with torch.cuda.stream(rule_stream):
             st_r = cur_stream(dev)
+            chain_done = self.chain is not None
+            if chain_done:
+                # the sites of EVERY strided level follow from the level-0 coordinates alone: three launches instead of
+                # mark + scan + emit (+ three memory operations) per level.  The sorted rows are the input (not the
+                # voxelizer's first-appearance order): neighbouring threads then mark neighbouring cells (23 vs 41 us)
+                ch = self.chain
+                check(L.bevf_spconv_strided_sites_chain(ptr(lv0.indices), lv0.cap, ptr(lv0.n_dev), self.batch, lv0.shape_c,
+                                                        ch["n"], ch["ks"], ch["st"], ch["pd"], ch["mems"], ch["bytes"],
+                                                        ch["outs"], ch["caps"], ch["ndevs"], st_r))
             for lv in self.levels:
                 lv.subm_fresh.clear()
             for op in self.ops:
@@ -261,10 +295,11 @@ class StaticFrontEnd:
                             op["ready"] = torch.cuda.Event()
                             op["ready"].record(rule_stream)
                 else:
-                    check(L.bevf_spconv_strided_sites(ptr(lin.indices), lin.cap, ptr(lin.n_dev), self.batch,
-                                                      lin.shape_c, ks, st_, pd, dl, ptr(lout.index_mem),
-                                                      ctypes.c_size_t(lout.index_bytes), ptr(lout.indices), lout.cap,
-                                                      ptr(lout.n_dev), st_r))
+                    if not chain_done:
+                        check(L.bevf_spconv_strided_sites(ptr(lin.indices), lin.cap, ptr(lin.n_dev), self.batch,
+                                                          lin.shape_c, ks, st_, pd, dl, ptr(lout.index_mem),
+                                                          ctypes.c_size_t(lout.index_bytes), ptr(lout.indices), lout.cap,
+                                                          ptr(lout.n_dev), st_r))
                     check(L.bevf_spconv_strided_rulebook(ptr(lout.indices), lout.cap, ptr(lout.n_dev), self.batch,
                                                          lin.shape_c, ks, st_, pd, dl, ptr(lin.index_mem),
                                                          ctypes.c_size_t(lin.index_bytes), None, ptr(pair), lout.ld,

@@ -312,6 +312,16 @@ int bevf_spconv_strided_sites(const int *in_indices, int n_in, const int *n_in_d
                               int *out_indices, int cap, int *n_out_dev, void *stream);
 /* step 2: pair_fwd[k, j] = row of the input at out[j]*stride - pad + k*dil, or -1.  n_out may be given on the
  * host, or (n_out_dev != NULL) read from the device with rows >= *n_out_dev left untouched. */
+/* The output sites of a CHAIN of strided convolutions (dilation 1), all levels at once, from the coordinates of the level
+ * below the first one (any row order, e.g. the voxelizer's): level l's sites are the union over the level-0 sites of the
+ * box each reaches on level l, and that box follows per axis from its box one level down -- so one pass over the
+ * level-0 coordinates marks every level's bitmap, and the rank scans and site lists of all levels are one launch each
+ * (same results as nlev calls of bevf_spconv_strided_sites, level after level).  ksizes / strides / paddings: [nlev, 3];
+ * index_mems / index_bytes / out_indices / caps / n_out_devs: one entry per level (host arrays). */
+int bevf_spconv_strided_sites_chain(const int *coords0, int n0, const int *n0_dev, int batch, const int *shape0, int nlev,
+                                    const int *ksizes, const int *strides, const int *paddings, void *const *index_mems,
+                                    const size_t *index_bytes, int *const *out_indices, const int *caps,
+                                    int *const *n_out_devs, void *stream);
 int bevf_spconv_strided_rulebook(const int *out_indices, int n_out, const int *n_out_dev, int batch,
                                  const int *in_shape_host, const int *ksize_host, const int *stride_host,
                                  const int *padding_host, const int *dilation_host, const void *in_index_mem,
