@@ -82,6 +82,47 @@ def get_indice_pairs(x, ksize, stride, padding, dilation, subm):
                           out_index, ksize, stride, padding, dilation, False)
 
 
+def strided_sites_chain(indices, batch_size, spatial_shape, convs):
+    """Output sites of a chain of strided convolutions (dilation 1), all levels in three launches
+    (bevf_spconv_strided_sites_chain).  indices [n, 4] int32 (b, x, y, z) in any order; convs = [(ksize, stride, padding),
+    ...].  -> [(out_indices [n_l, 4] in ascending cell order, out_shape)] per level: what get_indice_pairs(...).out_indices
+    gives when the convolutions are applied one after the other."""
+    dev = indices.device
+    L = lib()
+    n = len(convs)
+    shapes, shape = [], list(spatial_shape)
+    for ks, st_, pd in convs:
+        shape = conv_out_shape(shape, ks, st_, pd, (1, 1, 1))
+        shapes.append(shape)
+    n_in = int(indices.shape[0])
+    caps, cap = [], max(1, n_in)
+    for (ks, st_, pd), shp in zip(convs, shapes):
+        reach = 1
+        for k, s_ in zip(ks, st_):
+            reach *= min(k, -(-k // s_))
+        cap = max(1, min(cap * reach, batch_size * shp[0] * shp[1] * shp[2]))
+        caps.append(cap)
+    mems, nbytes = [], []
+    for shp in shapes:
+        b = int(L.bevf_spconv_index_bytes(batch_size, i32_array(shp)))
+        if b == 0:
+            raise RuntimeError("sparse grid not supported: " + L.bevf_last_error().decode())
+        nbytes.append(b)
+        mems.append(torch.empty(b, dtype=torch.uint8, device=dev))
+    outs = [torch.empty((c, 4), dtype=torch.int32, device=dev) for c in caps]
+    ndev = torch.zeros(n, dtype=torch.int32, device=dev)
+    flat = lambda j: (ctypes.c_int * (3 * n))(*[int(v) for c in convs for v in c[j]])
+    with torch.cuda.device(dev):
+        check(L.bevf_spconv_strided_sites_chain(
+            ptr(indices), n_in, None, int(batch_size), i32_array(list(spatial_shape)), n, flat(0), flat(1), flat(2),
+            (ctypes.c_void_p * n)(*[m.data_ptr() for m in mems]), (ctypes.c_size_t * n)(*nbytes),
+            (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs]), (ctypes.c_int * n)(*caps),
+            (ctypes.c_void_p * n)(*[ndev[l:].data_ptr() for l in range(n)]), cur_stream(dev)))
+    counts = ndev.tolist()
+    assert all(c <= cap for c, cap in zip(counts, caps))
+    return [(o[:c], shp) for o, c, shp in zip(outs, counts, shapes)]
+
+
 def pack_weight_f32(weight):
     """[Cout, kD, kH, kW, Cin] fp32 -> [kv, Cin, Cout] fp32."""
     cout, cin = weight.shape[0], weight.shape[-1]

@@ -102,3 +102,50 @@ def test_rulebook_and_fp32_conv_random_geometries(oracle_mod, case):
     assert got.shape == ref.shape
     if ref.size:
         assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+@st.composite
+def chain_cases(draw):
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    nlev = draw(st.integers(1, 4))
+    convs = []
+    for _ in range(nlev):
+        ks = tuple(draw(st.sampled_from([1, 2, 3])) for _ in range(3))
+        stride = tuple(draw(st.sampled_from([1, 2, 3])) for _ in range(3))
+        pad = tuple(draw(st.integers(0, 1)) for _ in range(3))
+        convs.append((ks, stride, pad))
+    shape = tuple(draw(st.integers(6, 40)) for _ in range(3))
+    batch = draw(st.integers(1, 3))
+    cells = batch * shape[0] * shape[1] * shape[2]
+    n = draw(st.integers(0, min(cells, 1500)))
+    lin = rng.choice(cells, size=n, replace=False)            # unsorted: the chain takes rows in any order
+    idx = np.stack([lin // (shape[0] * shape[1] * shape[2]), (lin // (shape[1] * shape[2])) % shape[0],
+                    (lin // shape[2]) % shape[1], lin % shape[2]], 1).astype(np.int32).reshape(-1, 4)
+    return convs, shape, batch, idx
+
+
+@settings(**COMMON)
+@given(chain_cases())
+def test_strided_sites_chain_equals_level_by_level(oracle_mod, case):
+    """bevf_spconv_strided_sites_chain (all levels from the level-0 coordinates: per-axis interval composition) against the
+    oracle's rulebook applied level after level, on random chains of strided convolutions (kernel 1-3, stride 1-3, padding
+    0-1 per axis: includes kernels smaller than the stride, i.e. gaps) and unsorted input rows."""
+    convs, shape, batch, idx = case
+    cur_shape, ok = list(shape), True
+    for ks, stride, pad in convs:                         # skip chains whose grid collapses
+        cur_shape = [(cur_shape[j] + 2 * pad[j] - (ks[j] - 1) - 1) // stride[j] + 1 for j in range(3)]
+        ok &= all(v >= 1 for v in cur_shape)
+    if not ok:
+        return
+    got = Fsp.strided_sites_chain(torch.from_numpy(idx).cuda(), batch, list(shape), convs)
+    cur_idx, cur_shape = idx, list(shape)
+    for (ks, stride, pad), (g_idx, g_shape) in zip(convs, got):
+        if cur_idx.shape[0]:
+            o_idx, _, o_shape = oracle_mod.spconv_rulebook(cur_idx, cur_shape, ks, stride, pad, (1, 1, 1), False)
+        else:
+            o_idx = np.zeros((0, 4), np.int32)
+            o_shape = [(cur_shape[j] + 2 * pad[j] - (ks[j] - 1) - 1) // stride[j] + 1 for j in range(3)]
+        assert [int(v) for v in g_shape] == [int(v) for v in o_shape]
+        np.testing.assert_array_equal(g_idx.cpu().numpy(), o_idx)
+        cur_idx, cur_shape = o_idx, [int(v) for v in o_shape]
