@@ -70,7 +70,9 @@ class BaseViewTransform(nn.Module):
         return pts
 
     def get_cam_feats(self, x):
-        raise NotImplementedError
+        """The conv stacks (dtransform / depthnet: dense cuDNN work) stay with the caller; the data path around them is
+        BaseDepthTransform.get_cam_feats below."""
+        raise NotImplementedError("BaseViewTransform has no depth network; see BaseDepthTransform.get_cam_feats")
 
     def bev_pool_aux(self, geom_feats):
         """depth_lss.py:118-176: quantise (truncation toward zero), drop out-of-grid points, rank, sort.
@@ -141,3 +143,21 @@ class BaseDepthTransform(BaseViewTransform):
         """depth [B, N, 1, H, W] -> (gt_depth_distr, counts_3d), each [B, N, fH, fW, D] (depth_lss.py:632-661)"""
         counts, distr = depth_histogram(depth, self.feature_size, self.dbound, self.D)
         return distr, counts
+
+    def get_cam_feats(self, x, d, dtransform, depthnet):
+        """DepthLSSTransform.get_cam_feats (depth_lss.py:617-725) with the frustum outer product left to the fused pooling:
+        x [B, N, C_img, fH, fW] image features, d [B, N, 1, H, W] LiDAR depth image (`lidar_depth`); `dtransform` and
+        `depthnet` are the caller's conv stacks (the reference's own modules: dense cuDNN work, out of scope here).
+        -> (depth [B*N, D, fH, fW], ctx [B*N, C, fH, fW], est_depth_distr, gt_depth_distr, counts_3d): depth / ctx go to
+        `pool_fused`; the other three are what the reference returns for its depth loss.  In training the softmax depth
+        is lifted to the LiDAR distribution with the correction detached (:702-706)."""
+        B, N, C_img, fH, fW = x.shape
+        gt_depth_distr, counts_3d = self.depth_distribution(d)                       # :632-661 (depth_prep.cu)
+        d = dtransform(d.view(B * N, *d.shape[2:]))
+        y = depthnet(torch.cat([d, x.view(B * N, C_img, fH, fW)], dim=1))            # [B*N, D + C, fH, fW]
+        depth = y[:, :self.D].softmax(dim=1)
+        est_depth_distr = depth.permute(0, 2, 3, 1).reshape(B, N, fH, fW, self.D)
+        if self.training:
+            depth_aux = gt_depth_distr.view(B * N, fH, fW, self.D).permute(0, 3, 1, 2)
+            depth = depth + (torch.maximum(depth_aux, depth) - depth).detach()
+        return depth, y[:, self.D:self.D + self.C], est_depth_distr, gt_depth_distr, counts_3d

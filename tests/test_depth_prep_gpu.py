@@ -106,3 +106,43 @@ def test_empty_and_behind_camera_points(oracle_mod):
         ops.depth_histogram(torch.zeros(1, 1, 64, 176), (8, 22), [1.0, 30.0, 0.5])
     with pytest.raises(Exception, match="multiple"):
         ops.depth_histogram(torch.zeros(1, 1, 60, 176, device="cuda"), (8, 22), [1.0, 30.0, 0.5])
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_get_cam_feats_data_path_and_fused_pooling(training):
+    """BaseDepthTransform.get_cam_feats + pool_fused against the reference's own sequence (depth_lss.py:617-725 followed by
+    bev_pool, :179-204) written out in torch: same conv stacks, outer product materialised, boundary-form pooling."""
+    torch.manual_seed(3)
+    g = golden("depth_prep.npz")
+    H, W = (int(v) for v in g["image_size"])
+    fH, fW = (int(v) for v in g["feature_size"])
+    C_img, C = 12, 16
+    vt = BaseDepthTransform(C_img, C, (H, W), (fH, fW), [-12.0, 12.0, 0.75], [-12.0, 12.0, 0.75], [-10.0, 10.0, 20.0],
+                            [float(v) for v in g["dbound"]]).cuda()
+    vt.train(training)
+    B, N = g["depth"].shape[:2]
+    d_img = _cuda(g["depth"])                                      # [B, N, 1, H, W]
+    x = torch.randn(B, N, C_img, fH, fW, device="cuda")
+    sh, sw = H // fH, W // fW
+    dtransform = torch.nn.Sequential(torch.nn.Conv2d(1, 8, (sh, sw), stride=(sh, sw)), torch.nn.ReLU()).cuda()
+    depthnet = torch.nn.Conv2d(8 + C_img, vt.D + C, 1).cuda()
+    rig = {k: _cuda(v) for k, v in synthetic.camera_rig(N, (H, W), B).items()}
+    geom = vt.get_geometry(**rig)
+    tables = vt.build_tables(geom)
+    with torch.no_grad():
+        depth, ctx, est, gt, counts = vt.get_cam_feats(x, d_img, dtransform, depthnet)
+        got = vt.pool_fused(depth.contiguous(), ctx.contiguous(), tables)
+        # the reference's sequence
+        gt_ref, counts_ref = vt.depth_distribution(d_img)
+        y = depthnet(torch.cat([dtransform(d_img.view(B * N, 1, H, W)), x.view(B * N, C_img, fH, fW)], 1))
+        dep = y[:, :vt.D].softmax(1)
+        est_ref = dep.permute(0, 2, 3, 1).reshape(B, N, fH, fW, vt.D)
+        if training:
+            dep = dep + (torch.maximum(gt_ref.view(B * N, fH, fW, vt.D).permute(0, 3, 1, 2), dep) - dep)
+        frustum = (dep.unsqueeze(1) * y[:, vt.D:vt.D + C].unsqueeze(2)).view(B, N, C, vt.D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+        vt.eval()                                                   # boundary form without the autograd Function
+        want = vt.bev_pool(frustum.contiguous(), geom)
+    assert torch.equal(gt, gt_ref) and torch.equal(counts, counts_ref) and torch.equal(est, est_ref)
+    assert depth.shape == (B * N, vt.D, fH, fW) and ctx.shape == (B * N, C, fH, fW)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), float((got - want).abs().max())
