@@ -47,18 +47,21 @@ def build_norm_layer(cfg, num_features, postfix=""):
 
 
 def register_all():
-    """Register the B200 classes under the reference's names; returns True if mmengine's registry was updated."""
+    """Register the B200 classes under the reference's names (write_spconv2.py:21-38 registers ten conv classes: the two on
+    the BEVFusion path are built here, the other eight are registered too and raise NotImplementedError when constructed);
+    returns True if mmengine's registry was updated."""
     from . import spconv
     from .sparse_encoder import BEVFusionSparseEncoder
 
-    for cls, nm in ((spconv.SubMConv3d, "SubMConv3d"), (spconv.SparseConv3d, "SparseConv3d"),
-                    (BEVFusionSparseEncoder, "BEVFusionSparseEncoder")):
+    classes = [(spconv.SubMConv3d, "SubMConv3d"), (spconv.SparseConv3d, "SparseConv3d"),
+               (BEVFusionSparseEncoder, "BEVFusionSparseEncoder")] + [(c, c.__name__) for c in spconv.OFF_PATH_CLASSES]
+    for cls, nm in classes:
         _LOCAL[nm] = cls
+    spconv.SparseModule._version = 2      # write_spconv2.py:38 (the checkpoint shim lives in SparseModule._load_from_state_dict)
     try:
         from mmengine.registry import MODELS
     except Exception:
         return False
-    MODELS._register_module(spconv.SubMConv3d, "SubMConv3d", force=True)
-    MODELS._register_module(spconv.SparseConv3d, "SparseConv3d", force=True)
-    MODELS._register_module(BEVFusionSparseEncoder, "BEVFusionSparseEncoder", force=True)
+    for cls, nm in classes:
+        MODELS._register_module(cls, nm, force=True)
     return True

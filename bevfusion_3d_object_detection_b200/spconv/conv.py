@@ -272,3 +272,30 @@ class SparseConv3d(SparseConvolution):
         super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
                          indice_key=indice_key, algo=algo, fp32_accum=fp32_accum,
                          record_voxel_count=record_voxel_count, name=name, **kwargs)
+
+
+def _off_path(name, ndim, what):
+    """The other conv classes spconv exports and mmdet3d registers (write_spconv2.py:21-38): same names, but constructing
+    one says plainly that it is not on the BEV front-end hot path instead of failing later in a registry lookup."""
+
+    class _OffPath(SparseModule):
+        def __init__(self, *args, **kwargs):
+            super().__init__()
+            raise NotImplementedError(f"{name}: {what} sparse convolutions are not on the BEVFusion front-end hot path "
+                                      f"(only SubMConv3d / SparseConv3d are built; DESIGN.md 7)")
+
+    _OffPath.__name__ = _OffPath.__qualname__ = name
+    _OffPath.ndim = ndim
+    return _OffPath
+
+
+SparseConv2d = _off_path("SparseConv2d", 2, "2-D")
+SparseConv4d = _off_path("SparseConv4d", 4, "4-D")
+SubMConv2d = _off_path("SubMConv2d", 2, "2-D")
+SubMConv4d = _off_path("SubMConv4d", 4, "4-D")
+SparseConvTranspose2d = _off_path("SparseConvTranspose2d", 2, "transposed")
+SparseConvTranspose3d = _off_path("SparseConvTranspose3d", 3, "transposed")
+SparseInverseConv2d = _off_path("SparseInverseConv2d", 2, "inverse")
+SparseInverseConv3d = _off_path("SparseInverseConv3d", 3, "inverse")
+OFF_PATH_CLASSES = (SparseConv2d, SparseConv4d, SubMConv2d, SubMConv4d, SparseConvTranspose2d, SparseConvTranspose3d,
+                    SparseInverseConv2d, SparseInverseConv3d)
