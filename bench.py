@@ -270,6 +270,22 @@ class CpuFrontEnd:
                 f"oracle) + torch outer-product/index_add_ bev_pool")
 
 
+def arm_config(cfg, args, frame_bytes):
+    """The `config` object of the JSON line: built the same way by BOTH arms (the reference arm reports the configuration
+    of the comparison, i.e. this arm's, verbatim: same workload, same batch per step, same input rotation)."""
+    B = cfg["batch"]
+    if args.config == "train":
+        return dict(workload=cfg["workload"], frames_per_gpu_per_step=B, precision=args.precision,
+                    l2="inputs rotate over 2 distinct batches (%.0f MB > 126 MB L2)" % (2 * B * frame_bytes / 1e6),
+                    parallelism="frame-parallel; gradient buckets all-reduced over NCCL as they complete")
+    ring = max(2, int(np.ceil(1.25 * L2_BYTES / (frame_bytes * B))))
+    return dict(workload=cfg["workload"], frames_per_gpu_per_step=B, precision=args.precision,
+                mode="one CUDA graph per batch, device-side row counts, %d batch(es) in flight"
+                     % min(args.inflight, args.inflight_device),
+                l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (ring, ring * B * frame_bytes / 1e6),
+                parallelism="frame-parallel, no data-path collective")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -295,7 +311,8 @@ def run_reference(args, rank, world):
         sample += "; forward + backward by torch autograd through the same formulation"
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", impl="reference", config=dict(workload=cfg["workload"]),
+                dtype="f32", data="synthetic", impl="reference",
+                config=arm_config(cfg, args, sum(int(v.nbytes) for v in frames[0].values())),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=cpu.cores, kind=cpu.kind, sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -693,11 +710,7 @@ def run_frontend(args, rank, world, local_rank):
                 dtype=("bf16 sparse conv (fp32 accumulate) + fp32 voxelize/bev_pool" if args.precision == "bf16"
                        else "f32"),
                 data="synthetic",
-                config=dict(workload=cfg["workload"], frames_per_gpu_per_step=B, precision=args.precision,
-                            mode="one CUDA graph per batch, device-side row counts, %d batch(es) in flight"
-                                 % min(args.inflight, args.inflight_device),
-                            l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (ring, ring * B * frame_bytes / 1e6),
-                            parallelism="frame-parallel, no data-path collective"),
+                config=arm_config(cfg, args, frame_bytes),
                 e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps, output={"dense": "fp32 dense BEV maps", "bf16": "compact (bf16 dense maps, lossy)",
                                  "rows": "lossless fp32 rows: active LiDAR rows + coordinates, camera columns of the "
@@ -996,7 +1009,9 @@ def _train_measure(torch, dist, cfg, precision, dev, rank, world, steps, warmup,
         d["tflops"] = d["flops"] / max(d["ms"], 1e-9) / 1e9
         d["frac"] = d["tflops"] / pk["tc"]
     n_params = sum(p.numel() for p in step.params)
-    out.update(ms_no_allreduce=ms_nored, ms_forward_only=ms_fwd, ms_e2e=ms_e2e, h2d=h2d, families=fam,
+    fr0 = batches[0]
+    frame_bytes = (sum(int(p.nbytes) for p in fr0["points"]) + int(fr0["depth"].nbytes) + int(fr0["ctx"].nbytes)) // B
+    out.update(ms_no_allreduce=ms_nored, ms_forward_only=ms_fwd, ms_e2e=ms_e2e, h2d=h2d, families=fam, frame_bytes=frame_bytes,
                n_params=n_params, buckets=len(step.reducer.buckets), allreduce_launched=step.reducer.launched)
     out["summary"] = dict(
         frames_per_s=world * B * steps / (ms / 1e3), ms_per_step=ms / steps, batch_per_gpu=B, n_gpus=world,
@@ -1060,10 +1075,7 @@ def run_train(args, rank, world, local_rank):
                 dtype=("bf16 sparse conv operands (fp32 accumulate, fp32 master weights and gradients) + fp32 "
                        "voxelize/bev_pool/BatchNorm" if args.precision == "bf16" else "f32"),
                 data="synthetic",
-                config=dict(workload=cfg["workload"], frames_per_gpu_per_step=B, precision=args.precision,
-                            l2="inputs rotate over 2 distinct batches (158 MB > 126 MB L2)",
-                            parallelism="frame-parallel; %d gradient buckets (%.1f MB fp32) all-reduced over NCCL as "
-                                        "they complete" % (s["grad_buckets"], s["grad_bytes"] / 1e6)),
+                config=arm_config(cfg, args, r["frame_bytes"]),
                 e2e=dict(value=s["e2e_frames_per_s"], unit="frames/s", h2d_bytes_per_step=r["h2d"], d2h_bytes_per_step=4),
                 gpu_launches=r["launches"], roofline=roof, stages=dict(training=s), cpu_baseline=cpu_baseline,
                 clocks=clocks)
