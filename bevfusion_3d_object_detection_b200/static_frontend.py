@@ -356,8 +356,15 @@ class StaticFrontEnd:
         # 5. dense()+permute+view of the last level
         last = self.levels[self.ops[-1]["level_out"]]
         c_last = self.ops[-1]["conv"].out_channels
-        check(L.bevf_sparse_to_dense(ptr(cur["f32"]), ptr(last.indices), last.cap, ptr(last.n_dev), c_last, self.batch,
-                                     last.shape_c, ptr(self.lidar_bev), 1, st))
+        import os as _os
+        if c_last % 4 == 0 and _os.environ.get("BEVFRONT_BEV_INDEXED", "1") == "1":
+            # output-driven: every (channel, z) line of the map written once, zeros included (no memset, no scattered stores)
+            check(L.bevf_sparse_to_bev_indexed(ptr(cur["f32"]), last.cap, ptr(last.n_dev), c_last, self.batch, last.shape_c,
+                                               ptr(last.index_mem), ctypes.c_size_t(last.index_bytes), ptr(self.lidar_bev),
+                                               st))
+        else:
+            check(L.bevf_sparse_to_dense(ptr(cur["f32"]), ptr(last.indices), last.cap, ptr(last.n_dev), c_last, self.batch,
+                                         last.shape_c, ptr(self.lidar_bev), 1, st))
         # the same information as active rows (HostPipeline's lossless "rows" output reads these)
         self.last_rows, self.last_level = cur["f32"], last
         # 6. camera branch (already in flight on its own stream when overlapping)

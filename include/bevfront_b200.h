@@ -333,6 +333,12 @@ int bevf_sparse_to_dense(const float *feats, const int *indices, int n, const in
                          const int *shape_host, float *dense, int bev_layout, void *stream);
 /* The transpose of bevf_sparse_to_dense (its backward in training): feats[i, :] = the dense tensor at site i, for
  * either layout.  feats [n, c] is fully written for the first n (or *n_dev) rows. */
+/* The BEV tail of BEVFusionSparseEncoder (dense() -> permute(0, 1, 4, 2, 3) -> view(N, C*D, H, W), sparse_encoder.py:147-151)
+ * driven from the output side: bev[b, ch*Z + z, x, y] for EVERY cell, zeros included (no memset of the map needed), from the
+ * rows of a level whose coordinate index (index_mem: bevf_spconv_index_build / _strided_sites[_chain]) maps cell -> row,
+ * i.e. rows in ascending cell order.  Same values as bevf_sparse_to_dense(..., bev_layout = 1).  c % 4 == 0. */
+int bevf_sparse_to_bev_indexed(const float *feats, int n_cap, const int *n_dev, int c, int batch, const int *shape,
+                               const void *index_mem, size_t index_bytes, float *bev, void *stream);
 int bevf_dense_to_sparse(const float *dense, const int *indices, int n, const int *n_dev, int c, int batch,
                          const int *shape_host, int bev_layout, float *feats, void *stream);
 /* Rows re-ordered by perm (rank -> row, from bevf_spconv_index_build): out_indices[r] = indices[perm[r]]; features
