@@ -256,6 +256,37 @@ def spconv_rulebook(indices, spatial_shape, ksize, stride=1, padding=0, dilation
     return out_idx, pair[:, :n_out], out_shape
 
 
+def strided_chain_boxes(indices, spatial_shape, convs):
+    """Numpy / pure-Python restatement of the library's one-pass site construction for a CHAIN of strided convolutions
+    (csrc/spconv_rulebook.cu: mark_levels_kernel): the box a level-0 site reaches on level l follows per axis from its box on
+    level l-1 -- ceil((i0 + p - (k-1)) / s) .. floor((i1 + p) / s), clipped to the grid -- and level l's site set is the
+    union of the boxes.  convs = [(ksize, stride, padding), ...]; -> per level the sorted [n_l, 4] sites.  The test checks it
+    against spconv_rulebook applied level after level (the definition).  Small inputs only (Python loops)."""
+    indices = np.asarray(indices, np.int32).reshape(-1, 4)
+    shapes, shape = [], [int(v) for v in spatial_shape]
+    for ks, st, pd in convs:
+        shape = [int(v) for v in spconv_out_shape(shape, ks, st, pd, (1, 1, 1))]
+        shapes.append(shape)
+    sets = [set() for _ in convs]
+    for b, x, y, z in indices.tolist():
+        lo, hi = [x, y, z], [x, y, z]
+        for l, (ks, st, pd) in enumerate(convs):
+            empty = False
+            for a in range(3):
+                k, s, p = int(ks[a]), int(st[a]), int(pd[a])
+                nlo = max(-((-(lo[a] + p - (k - 1))) // s), 0)          # ceil division
+                nhi = min((hi[a] + p) // s, shapes[l][a] - 1)            # floor division
+                lo[a], hi[a] = nlo, nhi
+                empty |= nlo > nhi
+            if empty:
+                break
+            for xx in range(lo[0], hi[0] + 1):
+                for yy in range(lo[1], hi[1] + 1):
+                    for zz in range(lo[2], hi[2] + 1):
+                        sets[l].add((b, xx, yy, zz))
+    return [(np.array(sorted(s_), np.int32).reshape(-1, 4), shp) for s_, shp in zip(sets, shapes)]
+
+
 def spconv_gemm(feats, weight, pair_fwd, bias=None, acc_double=True):
     """weight [Cout, kD, kH, kW, Cin] (spconv-2.x layout) -> out[n_out, Cout]"""
     feats = _f32(feats)
