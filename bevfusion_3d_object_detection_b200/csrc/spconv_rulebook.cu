@@ -484,11 +484,11 @@ constexpr int kBevCh = 32;
 __global__ void __launch_bounds__(256)
     to_bev_indexed_kernel(const float *__restrict__ feats, const unsigned *__restrict__ bitmap,
                           const int *__restrict__ word_prefix, const int *__restrict__ n_dev, int n_cap, int c, Grid g,
-                          float *__restrict__ bev) {
+                          int tile_floats, float *__restrict__ bev) {
   extern __shared__ int sm_bev[];
   const int cells = g.y * g.z;
   int *rowidx = sm_bev;                                            // [y * Z + z] -> row or -1
-  float *tile = reinterpret_cast<float *>(sm_bev + cells);         // [rows of the line][kBevCh + 1]
+  float *tile = reinterpret_cast<float *>(sm_bev + cells);         // [rows of the line][channels of the pass + 1]
   __shared__ int s_r0, s_r1;
   const int x = blockIdx.x % g.x, chunk = blockIdx.x / g.x, b = blockIdx.y;
   const int ch0 = chunk * kBevCh, nch = min(kBevCh, c - ch0);
@@ -509,25 +509,33 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   const int r0 = s_r0, nrows = s_r1 - r0 + 1;                      // <= cells: the line's rows are consecutive
-  if (nrows > 0) {
-    const int vec = nch / 4;                                       // 16-byte pieces per row chunk (c % 4 == 0)
-    for (int e = threadIdx.x; e < nrows * vec; e += blockDim.x) {
-      const int r = e / vec, q = e - r * vec;
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(feats + (size_t)(r0 + r) * c + ch0) + q);
-      float *d = tile + r * (kBevCh + 1) + 4 * q;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-  }
-  __syncthreads();
+  // channels per pass: all of the chunk when the line's rows fit the tile (sized for ~90 % of a full line so that five
+  // CTAs share an SM and the grid is one wave), fewer -- a multiple of 4 -- for the rare fuller line
+  int gch = nch;
+  if (nrows > 0 && nrows * (nch + 1) > tile_floats) gch = max(4, ((tile_floats / nrows - 1) / 4) * 4);
   const size_t plane = (size_t)g.x * g.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int p = warp; p < nch * g.z; p += blockDim.x >> 5) {        // plane line (channel, z): ny contiguous floats
-    const int chl = p / g.z, z = p - chl * g.z;
-    float *o = bev + (((size_t)b * c + ch0 + chl) * g.z + z) * plane + (size_t)x * g.y;
-    for (int y = lane; y < g.y; y += 32) {
-      const int row = rowidx[y * g.z + z];
-      o[y] = row >= 0 ? tile[(row - r0) * (kBevCh + 1) + chl] : 0.f;
+  for (int c0 = 0; c0 < nch; c0 += gch) {
+    const int cn = min(gch, nch - c0), pitch = cn + 1;
+    if (nrows > 0) {
+      const int vec = cn / 4;                                      // 16-byte pieces per row chunk (c % 4 == 0)
+      for (int e = threadIdx.x; e < nrows * vec; e += blockDim.x) {
+        const int r = e / vec, q = e - r * vec;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(feats + (size_t)(r0 + r) * c + ch0 + c0) + q);
+        float *d = tile + r * pitch + 4 * q;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
     }
+    __syncthreads();
+    for (int p = warp; p < cn * g.z; p += blockDim.x >> 5) {       // plane line (channel, z): ny contiguous floats
+      const int chl = p / g.z, z = p - chl * g.z;
+      float *o = bev + (((size_t)b * c + ch0 + c0 + chl) * g.z + z) * plane + (size_t)x * g.y;
+      for (int y = lane; y < g.y; y += 32) {
+        const int row = rowidx[y * g.z + z];
+        o[y] = row >= 0 ? tile[(row - r0) * pitch + chl] : 0.f;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -887,7 +895,14 @@ BEVF_API int bevf_sparse_to_bev_indexed(const float *feats, int n_cap, const int
   carve_index(m, const_cast<void *>(index_mem), index_bytes, nwords);
   Grid g{batch, shape[0], shape[1], shape[2]};
   const size_t cells = (size_t)shape[1] * shape[2];
-  const size_t smem = cells * sizeof(int) + cells * (kBevCh + 1) * sizeof(float);
+  // tile: a full line x 32 channels when that keeps five CTAs on an SM (<= 44 KB), else what fits (at least 5 floats per
+  // row of a full line: the kernel then takes the channels in several passes)
+  size_t tile_floats = cells * (kBevCh + 1);
+  const size_t budget = 44 * 1024;
+  if (cells * sizeof(int) + tile_floats * sizeof(float) > budget && budget > cells * sizeof(int))
+    tile_floats = (budget - cells * sizeof(int)) / sizeof(float);
+  if (tile_floats < cells * 5) tile_floats = cells * 5;
+  const size_t smem = cells * sizeof(int) + tile_floats * sizeof(float);
   if (smem > 200 * 1024) {
     bevf::set_error("BEV tail: a line of %zu cells does not fit in shared memory", cells);
     return BEVF_ERR_UNSUPPORTED;
@@ -897,7 +912,7 @@ BEVF_API int bevf_sparse_to_bev_indexed(const float *feats, int n_cap, const int
     BEVF_CHECK_CUDA(cudaFuncSetAttribute(to_bev_indexed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int chunks = bevf::ceil_div(c, kBevCh);
   to_bev_indexed_kernel<<<dim3(shape[0] * chunks, batch), 256, smem, (cudaStream_t)stream>>>(
-      feats, m.bitmap, m.word_prefix, n_dev, n_cap, c, g, bev);
+      feats, m.bitmap, m.word_prefix, n_dev, n_cap, c, g, (int)tile_floats, bev);
   BEVF_CHECK_LAUNCH();
   return BEVF_OK;
 }

@@ -742,3 +742,35 @@ def test_block_training_gradients_match_torch_autograd(precision):
         close(x.grad, xr.grad, "input gradient")
         for name, ref in params.items():
             close(mine[name].grad, ref.grad, name)
+
+
+@pytest.mark.parametrize("shape,batch,fill,c", [((12, 180, 2), 1, 1.0, 128), ((12, 180, 2), 2, 0.5, 128),
+                                                ((7, 33, 5), 2, 0.9, 16), ((9, 20, 3), 1, 0.05, 36), ((6, 10, 4), 1, 0.0, 8)])
+def test_bev_tail_output_driven_equals_scatter_form(shape, batch, fill, c):
+    """bevf_sparse_to_bev_indexed (every line of the map written once through the coordinate index, zeros included, no
+    memset) against bevf_sparse_to_dense(bev_layout=1) -- dense() + permute + view of sparse_encoder.py:147-151 -- on full,
+    half-full, sparse and empty grids (the full 180 x 2 lines take the multi-pass path of the kernel)."""
+    import ctypes
+
+    from bevfusion_3d_object_detection_b200._lib import check, cur_stream, i32_array, lib, ptr
+    from bevfusion_3d_object_detection_b200.spconv.core import CoordIndex
+
+    rng = np.random.default_rng(11)
+    cells = batch * shape[0] * shape[1] * shape[2]
+    n = int(round(fill * cells))
+    idx = random_sites(rng, n, batch, shape, sort=True) if n else np.zeros((0, 4), np.int32)
+    buf = torch.from_numpy(rng.standard_normal((max(n, 1), c)).astype(np.float32)).cuda()   # capacity >= 1 row
+    feats = buf[:n]
+    ind = torch.from_numpy(idx).cuda()
+    L = lib()
+    dev = torch.device("cuda")
+    want = torch.empty((batch, c * shape[2], shape[0], shape[1]), device=dev)
+    got = torch.full_like(want, float("nan"))                       # the output-driven form must write every element
+    shape_c = i32_array(list(shape))
+    n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(L.bevf_sparse_to_dense(ptr(feats), ptr(ind), n, None, c, batch, shape_c, ptr(want), 1, cur_stream(dev)))
+        index = CoordIndex(ind, batch, shape, sorted_rows=True)
+        check(L.bevf_sparse_to_bev_indexed(ptr(buf), max(n, 1), ptr(n_dev), c, batch, shape_c, ptr(index.mem),
+                                           ctypes.c_size_t(index.nbytes), ptr(got), cur_stream(dev)))
+    assert torch.equal(got, want)
